@@ -1,0 +1,597 @@
+// bn_fit.cu -- per-gene maximum marginal likelihood of the binomial-thinned negative
+// binomial: the whole of BB_Fun (R/PRIOR_FUNCTIONS.R:380-549, FIX_MU=TRUE) as ONE kernel
+// launch instead of genes x evaluations .Call round trips into MarginalF_NB_1D
+// (src/bayNorm_main.cpp:928-943).
+//
+// Likelihood of gene i at size phi (mean mu_i fixed, m_j = mu_i * beta_j):
+//   l(phi) = sum_j log NB(x_ij; size phi, mean m_j)
+//          = -phi * sum_{all cells j} log1p(m_j/phi)                          [dense part, C terms]
+//            + sum_{x_ij > 0} { lgamma(x+phi) - lgamma(phi) + x*(log m_j - log(phi+m_j)) }
+//            - sum_{x_ij > 0} lgamma(x+1)                                     [constant in phi]
+// The x = 0 term phi*log(phi/(phi+m)) is what R's dnbinom_mu evaluates for zeros
+// (`size * log(size/(size+mu))` or its log1p twin); written as -phi*log1p(m/phi) it is
+// accurate in both regimes with no branch and no division per cell.
+//
+// Geometry: a group of TPG threads (one warp, or one 256-thread CTA for long genes) owns a
+// gene; groups pull genes from an atomic queue (iteration counts vary 10x between genes).
+// The optimiser state is replicated in every thread of the group (uniform control flow);
+// each evaluation is a group-wide FP64 reduction with a fixed summation order, so a gene's
+// result does not depend on which group ran it, on the grid size or on the GPU count.
+#include <math.h>
+
+#include "bn_internal.cuh"
+
+struct FitGene {
+    const int32_t *cell; // this gene's non-zeros
+    const double *rval;
+    int64_t nnz;
+    const double *beta, *logbeta;
+    int64_t C;
+    double mu, lmu, K; // K = sum lgamma(x+1)
+};
+
+// lgamma(x+phi) - lgamma(phi) for integer x >= 1
+__device__ __forceinline__ double lgamma_delta(double x, double phi, double lgphi)
+{
+    if (x <= 8.0) {
+        double p = phi;
+        for (double k = 1.0; k < x; k += 1.0) p *= (phi + k);
+        return log(p);
+    }
+    return lgamma(x + phi) - lgphi;
+}
+
+template <int TPG> __device__ double nb_loglik(const FitGene &g, double phi, double *scratch, int tid)
+{
+    const double r = g.mu / phi;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t j = tid;
+    for (; j + 3 * TPG < g.C; j += 4 * TPG) {
+        a0 += log1p(r * __ldg(g.beta + j));
+        a1 += log1p(r * __ldg(g.beta + j + TPG));
+        a2 += log1p(r * __ldg(g.beta + j + 2 * TPG));
+        a3 += log1p(r * __ldg(g.beta + j + 3 * TPG));
+    }
+    for (; j < g.C; j += TPG) a0 += log1p(r * __ldg(g.beta + j));
+    double acc = -phi * ((a0 + a1) + (a2 + a3));
+    const double lgphi = lgamma(phi);
+    double sp = 0.0;
+    for (int64_t k = tid; k < g.nnz; k += TPG) {
+        const int32_t c = g.cell[k];
+        const double x = g.rval[k];
+        const double m = g.mu * __ldg(g.beta + c);
+        sp += x * ((g.lmu + __ldg(g.logbeta + c)) - log(phi + m)) + lgamma_delta(x, phi, lgphi);
+    }
+    return bn_group_sum<TPG>(acc + sp, scratch) - g.K;
+}
+
+// d l / d phi = sum_j [ digamma(x+phi) - digamma(phi) + log(phi/(phi+m_j)) + (m_j - x)/(m_j + phi) ]
+// (GradientFun_NB_1D, src/bayNorm_main.cpp:972-987)
+__device__ __forceinline__ double bn_digamma(double x)
+{
+    double r = 0.0;
+    while (x < 10.0) {
+        r -= 1.0 / x;
+        x += 1.0;
+    }
+    const double f = 1.0 / (x * x);
+    const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+    return r + log(x) - 0.5 / x + t;
+}
+
+template <int TPG> __device__ double nb_loglik_grad(const FitGene &g, double phi, double *scratch, int tid)
+{
+    const double r = g.mu / phi;
+    double acc = 0.0;
+    for (int64_t j = tid; j < g.C; j += TPG) {
+        const double t = r * __ldg(g.beta + j); // m/phi
+        acc += t / (1.0 + t) - log1p(t);        // log(phi/(phi+m)) + m/(m+phi)
+    }
+    const double dgphi = bn_digamma(phi);
+    double sp = 0.0;
+    for (int64_t k = tid; k < g.nnz; k += TPG) {
+        const double x = g.rval[k];
+        const double m = g.mu * __ldg(g.beta + g.cell[k]);
+        double dd;
+        if (x <= 16.0) {
+            dd = 0.0;
+            for (double q = 0.0; q < x; q += 1.0) dd += 1.0 / (phi + q);
+        } else
+            dd = bn_digamma(x + phi) - dgphi;
+        sp += dd - x / (m + phi);
+    }
+    return bn_group_sum<TPG>(acc + sp, scratch);
+}
+
+// ---------------------------------------------------------------------------------
+// Solvers as resumable state machines: `next` is the point to evaluate, step(value) consumes
+// -l(next) (or -dl/dphi when next_is_grad) and either asks for another point (true) or is
+// finished (false).  One evaluation site in the kernel keeps the code small (the likelihood
+// body is ~1.5k instructions) and every thread of the group steps the same state.
+//
+// SpgState is BB::spg restated for one bounded parameter (see oracle/baynorm_oracle.c:
+// orc_spg for the line-by-line CPU twin and the provenance of every constant);
+// control$maximize = TRUE, so the objective is func = -l.
+// ---------------------------------------------------------------------------------
+struct FitOpts {
+    int method, maxfeval, maxit, M, use_gradient;
+    double ftol, gtol, eps, xatol;
+};
+
+__device__ __forceinline__ double proj(double p, double lo, double hi) { return p < lo ? lo : (p > hi ? hi : p); }
+
+struct SpgState {
+    enum { INIT_F = 0, INIT_G = 1, LS = 2, GRAD = 3 };
+    double lower, upper;
+    double lastfv[16];
+    double par, f, gr, lambda, pbest, fbest, fchg, pginfn;
+    double d, gtd, fmaxv, alpha, pnew;
+    int phase, iter, feval, lsflag, M;
+    bool ls_first;
+    // outputs / requests
+    double next;
+    bool next_is_grad;
+    int conv;
+
+    __device__ void init(double par0, double lo, double hi, const FitOpts &o)
+    {
+        lower = lo;
+        upper = hi;
+        M = o.M > 16 ? 16 : (o.M < 1 ? 1 : o.M);
+#pragma unroll
+        for (int i = 0; i < 16; i++) lastfv[i] = -1e99;
+        iter = 0;
+        feval = 0;
+        lsflag = -1;
+        fchg = INFINITY;
+        lambda = 1.0;
+        par = proj(par0, lo, hi);
+        pbest = par;
+        phase = INIT_F;
+        next = par;
+        next_is_grad = false;
+        conv = 0;
+    }
+    __device__ __forceinline__ void ask_grad(double at, const FitOpts &o)
+    {
+        next_is_grad = o.use_gradient != 0;
+        next = next_is_grad ? at : at + o.eps;
+    }
+    __device__ __forceinline__ bool finish()
+    {
+        if (lsflag <= 0) conv = 0; // iter >= maxit handled by the caller of finish()
+        else conv = (lsflag == 1) ? 3 : (lsflag == 2) ? 2 : (lsflag == 3) ? 4 : 5;
+        next = pbest;
+        return false;
+    }
+    // start the next outer iteration or stop (the `while` header of spg)
+    __device__ bool enter_iter(const FitOpts &o)
+    {
+        if (!(pginfn > o.gtol && iter <= o.maxit && fchg > o.ftol)) {
+            const bool r = finish();
+            if (lsflag <= 0 && iter >= o.maxit) conv = 1;
+            return r;
+        }
+        iter++;
+        d = proj(par - lambda * gr, lower, upper) - par;
+        gtd = gr * d;
+        if (isinf(gtd)) {
+            lsflag = 4;
+            return finish();
+        }
+        fmaxv = lastfv[0];
+#pragma unroll
+        for (int i = 1; i < 16; i++)
+            if (i < M && lastfv[i] > fmaxv) fmaxv = lastfv[i];
+        alpha = 1.0;
+        pnew = par + alpha * d;
+        phase = LS;
+        ls_first = true;
+        next = pnew;
+        next_is_grad = false;
+        return true;
+    }
+    __device__ bool step(double v, const FitOpts &o)
+    {
+        const double lmin = 1e-30, lmax = 1e30;
+        switch (phase) {
+        case INIT_F: {
+            f = v;
+            feval++;
+            if (f != f || isinf(f)) {
+                conv = 3;
+                next = par;
+                return false;
+            }
+            fbest = f;
+            phase = INIT_G;
+            ask_grad(par, o);
+            return true;
+        }
+        case INIT_G: {
+            gr = next_is_grad ? v : (v - f) / o.eps;
+            if (gr != gr) {
+                conv = 4;
+                next = par;
+                return false;
+            }
+            lastfv[0] = f;
+            pginfn = fabs(proj(par - gr, lower, upper) - par);
+            if (pginfn != 0.0) lambda = fmin(lmax, fmax(lmin, 1.0 / pginfn));
+            return enter_iter(o);
+        }
+        case LS: {
+            const double fnew = v;
+            feval++;
+            lsflag = 0;
+            if (fnew != fnew) {
+                lsflag = 1;
+                return finish();
+            }
+            if (!ls_first && feval > o.maxfeval) {
+                lsflag = 2;
+                return finish();
+            }
+            ls_first = false;
+            if (fnew > fmaxv + 1e-4 * alpha * gtd) { // nonmonotone Armijo test failed: backtrack
+                if (alpha <= 0.1) alpha = alpha / 2;
+                else {
+                    double atemp = -(gtd * alpha * alpha) / (2 * (fnew - f - alpha * gtd));
+                    if (atemp < 0.1 || atemp > 0.9 * alpha) atemp = alpha / 2;
+                    alpha = atemp;
+                }
+                pnew = par + alpha * d;
+                next = pnew;
+                next_is_grad = false;
+                return true;
+            }
+            fchg = fabs(f - fnew);
+            f = fnew;
+            const int slot = iter % M;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i == slot) lastfv[i] = f;
+            phase = GRAD;
+            ask_grad(pnew, o);
+            return true;
+        }
+        default: { // GRAD
+            const double gnew = next_is_grad ? v : (v - f) / o.eps;
+            if (gnew != gnew) {
+                lsflag = 3;
+                return finish();
+            }
+            const double s = pnew - par, y = gnew - gr;
+            par = pnew;
+            gr = gnew;
+            const double sts = s * s, yty = y * y;
+            lambda = (sts == 0.0 || yty == 0.0) ? lmax : fmin(lmax, fmax(lmin, sqrt(sts / yty)));
+            pginfn = fabs(proj(par - gr, lower, upper) - par);
+            if (f < fbest) {
+                fbest = f;
+                pbest = pnew;
+            }
+            return enter_iter(o);
+        }
+        }
+    }
+};
+
+// Bounded Brent (golden section + parabolic interpolation) on -l: the "argmax" solver the
+// north star names; not what the reference runs, offered as opts.method = BN_FIT_BRENT.
+struct BrentState {
+    double a, b, x, w, v, fx, fw, fv, d, e, u;
+    int it, conv;
+    bool first;
+    double next;
+
+    __device__ void init(double lo, double hi)
+    {
+        a = lo;
+        b = hi;
+        d = e = 0.0;
+        x = w = v = a + 0.3819660112501051 * (b - a);
+        it = 0;
+        conv = 1;
+        first = true;
+        next = x;
+    }
+    // choose the next trial point or stop
+    __device__ bool propose(const FitOpts &o)
+    {
+        const double golden = 0.3819660112501051;
+        if (it >= o.maxfeval) {
+            next = x;
+            return false;
+        }
+        it++;
+        const double xm = 0.5 * (a + b), tol1 = 1.4901161193847656e-08 * fabs(x) + o.xatol / 3.0, tol2 = 2.0 * tol1;
+        if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) {
+            conv = 0;
+            next = x;
+            return false;
+        }
+        bool golden_step = true;
+        if (fabs(e) > tol1) {
+            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pp = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) pp = -pp;
+            q = fabs(q);
+            r = e;
+            e = d;
+            if (fabs(pp) < fabs(0.5 * q * r) && pp > q * (a - x) && pp < q * (b - x)) {
+                d = pp / q;
+                const double ut = x + d;
+                if ((ut - a) < tol2 || (b - ut) < tol2) d = (xm - x >= 0) ? tol1 : -tol1;
+                golden_step = false;
+            }
+        }
+        if (golden_step) {
+            e = (x >= xm) ? a - x : b - x;
+            d = golden * e;
+        }
+        u = (fabs(d) >= tol1) ? x + d : x + ((d >= 0) ? tol1 : -tol1);
+        next = u;
+        return true;
+    }
+    __device__ bool step(double fu, const FitOpts &o)
+    {
+        if (first) {
+            first = false;
+            fx = fw = fv = fu;
+            return propose(o);
+        }
+        if (fu <= fx) {
+            if (u >= x) a = x;
+            else b = x;
+            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+        } else {
+            if (u < x) a = u;
+            else b = u;
+            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+        return propose(o);
+    }
+};
+
+template <int TPG>
+__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG)
+    k_fit_size(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ cell,
+               const double *__restrict__ rval, const double *__restrict__ beta, const double *__restrict__ logbeta,
+               const double *__restrict__ mu0, const double *__restrict__ size0, double lower, double upper, FitOpts o,
+               unsigned long long *__restrict__ queue, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
+               int32_t *__restrict__ nfe_out)
+{
+    __shared__ double scratch[8];
+    __shared__ unsigned long long next_gene;
+    const int tid = (TPG == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    for (;;) {
+        unsigned long long gq;
+        if (TPG == 32) {
+            if (tid == 0) gq = atomicAdd(queue, 1ULL);
+            gq = __shfl_sync(0xffffffffu, gq, 0);
+        } else {
+            __syncthreads();
+            if (tid == 0) next_gene = atomicAdd(queue, 1ULL);
+            __syncthreads();
+            gq = next_gene;
+        }
+        if (gq >= (unsigned long long)G) break;
+        const int64_t gi = (int64_t)gq;
+        FitGene g;
+        const int64_t a = rowptr[gi];
+        g.cell = cell + a;
+        g.rval = rval + a;
+        g.nnz = rowptr[gi + 1] - a;
+        g.beta = beta;
+        g.logbeta = logbeta;
+        g.C = C;
+        g.mu = mu0[gi];
+        g.lmu = log(g.mu);
+        double par = size0[gi], res = par;
+        int conv = 0, nfe = 0;
+        if (g.nnz == 0 || !(g.mu > 0.0)) {
+            // flat likelihood (all-zero gene): spg's first projected gradient is 0, it returns the start
+            res = proj(par, lower, upper);
+            if (o.method == BN_FIT_SPG) nfe = 2;
+        } else {
+            double kk = 0.0;
+            for (int64_t k = tid; k < g.nnz; k += TPG) kk += lgamma(g.rval[k] + 1.0);
+            g.K = bn_group_sum<TPG>(kk, scratch);
+            if (o.method == BN_FIT_BRENT) {
+                BrentState st;
+                st.init(lower, upper);
+                bool more = true;
+                while (more) {
+                    const double val = -nb_loglik<TPG>(g, st.next, scratch, tid);
+                    nfe++;
+                    more = st.step(val, o);
+                }
+                res = st.next;
+                conv = st.conv;
+            } else {
+                SpgState st;
+                st.init(par, lower, upper, o);
+                bool more = true;
+                while (more) {
+                    double val;
+                    if (st.next_is_grad) val = -nb_loglik_grad<TPG>(g, st.next, scratch, tid);
+                    else val = -nb_loglik<TPG>(g, st.next, scratch, tid);
+                    nfe++;
+                    more = st.step(val, o);
+                }
+                res = st.next;
+                conv = st.conv;
+            }
+        }
+        if (tid == 0) {
+            size_out[gi] = res;
+            if (conv_out) conv_out[gi] = conv;
+            if (nfe_out) nfe_out[gi] = nfe;
+        }
+    }
+}
+
+__global__ void k_log_vec(int64_t n, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = log(in[k]);
+}
+
+extern "C" void bn_fit_opts_default(bn_fit_opts *o)
+{
+    if (!o) return;
+    o->method = BN_FIT_SPG;
+    o->maxfeval = 500;
+    o->maxit = 1500;
+    o->M = 10;
+    o->ftol = 1e-10;
+    o->gtol = 1e-5;
+    o->eps = 1e-7;
+    o->xatol = 1e-10;
+    o->use_gradient = 0;
+    o->reserved = 0;
+}
+
+// device-pointer core shared by bn_fit_size and bn_prior.  lower/upper are host scalars.
+int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const double *d_mu0, const double *d_size0,
+                       double lower, double upper, const bn_fit_opts *opts, double *d_size_out, int32_t *d_conv,
+                       int32_t *d_nfe)
+{
+    if (!m->is_count)
+        return bn_fail(ctx, BN_ERR_NONCOUNT, "the likelihood fit needs non-negative integer counts (dnbinom_mu is 0 elsewhere)");
+    if (!(lower > 0.0) || !(upper >= lower)) return bn_fail(ctx, BN_ERR_INVALID, "bad size bounds [%g, %g]", lower, upper);
+    bn_fit_opts od;
+    bn_fit_opts_default(&od);
+    if (opts) od = *opts;
+    FitOpts o;
+    o.method = od.method;
+    o.maxfeval = od.maxfeval;
+    o.maxit = od.maxit;
+    o.M = od.M;
+    o.use_gradient = od.use_gradient;
+    o.ftol = od.ftol;
+    o.gtol = od.gtol;
+    o.eps = od.eps;
+    o.xatol = od.xatol;
+    BN_TRY(bn_mat_ensure_csr(ctx, m));
+    DevBuf<double> lb;
+    BN_TRY(lb.alloc(ctx, (size_t)m->C));
+    BN_LAUNCH(ctx, k_log_vec, (unsigned)((m->C + 255) / 256), 256, 0, m->C, d_beta, lb.p);
+    DevBuf<unsigned long long> q;
+    BN_TRY(q.alloc(ctx, 1));
+    BN_CUDA(ctx, cudaMemsetAsync(q.p, 0, 8, ctx->stream));
+    const int sms = ctx->prop.multiProcessorCount;
+    if (m->C >= 8192) {
+        // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
+        const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 8);
+        BN_LAUNCH(ctx, k_fit_size<256>, grid, 256, 0, m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0,
+                  lower, upper, o, q.p, d_size_out, d_conv, d_nfe);
+    } else {
+        const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 16);
+        BN_LAUNCH(ctx, k_fit_size<32>, grid, 128, 0, m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0,
+                  lower, upper, o, q.p, d_size_out, d_conv, d_nfe);
+    }
+    return BN_OK;
+}
+
+extern "C" int bn_fit_size(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const double *INITIAL_MU_vec,
+                           const double *INITIAL_SIZE_vec, double SIZE_lower, double SIZE_upper, const bn_fit_opts *opts,
+                           double *size_out, int32_t *conv, int32_t *nfeval)
+{
+    if (!ctx || !m || !BETA_vec || !INITIAL_MU_vec || !INITIAL_SIZE_vec || !size_out)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_fit_size: NULL argument") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> b, mu0, s0;
+    BN_TRY(b.bind(ctx, BETA_vec, (size_t)m->C));
+    BN_TRY(mu0.bind(ctx, INITIAL_MU_vec, (size_t)m->G));
+    BN_TRY(s0.bind(ctx, INITIAL_SIZE_vec, (size_t)m->G));
+    DevOut<double> so;
+    DevOut<int32_t> co, no;
+    BN_TRY(so.bind(ctx, size_out, (size_t)m->G));
+    BN_TRY(co.bind(ctx, conv, (size_t)m->G));
+    BN_TRY(no.bind(ctx, nfeval, (size_t)m->G));
+    BN_TRY(bn_fit_size_device(ctx, m, b.p, mu0.p, s0.p, SIZE_lower, SIZE_upper, opts, so.p, co.p, no.p));
+    BN_TRY(so.commit(ctx));
+    BN_TRY(co.commit(ctx));
+    BN_TRY(no.commit(ctx));
+    return bn_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------
+// single-gene entry points on a dense count vector (the registered .Call routines
+// MarginalF_NB_1D/2D and GradientFun_NB_1D/2D).  One CTA, fixed-order reduction.
+// ---------------------------------------------------------------------------------
+// which: 0 = log-likelihood, 1 = d/dsize, 2 = d/dmu
+__global__ void __launch_bounds__(1024) k_dense_gene(int which, double size, double mu, const double *__restrict__ x,
+                                                     const double *__restrict__ beta, int64_t n, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    const double lgs = lgamma(size), dgs = (which == 1) ? bn_digamma(size) : 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double xv = x[j], m = beta[j] * mu;
+        double t;
+        if (which == 0) {
+            if (xv < 0.0 || xv != floor(xv)) t = -INFINITY; // R_D_nonint_check / x < 0: density 0
+            else if (xv == 0.0) t = -size * log1p(m / size);
+            else
+                t = lgamma(xv + size) - lgs - lgamma(xv + 1.0) - size * log1p(m / size) + xv * (log(m) - log(size + m));
+        } else if (which == 1) {
+            t = bn_digamma(xv + size) - dgs + log(size / (size + m)) + (m - xv) / (m + size);
+        } else {
+            t = (xv * size - m * size) / (mu * (m + size));
+        }
+        acc += t;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    acc = bn_warp_sum(acc);
+    if (lane == 0) sh[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) s += sh[k];
+        out[0] = s;
+    }
+}
+
+static int dense_gene(bn_ctx *ctx, int which, double size, double mu, const double *x, const double *beta, int64_t n,
+                      double *out)
+{
+    if (!ctx || !x || !beta || !out || n <= 0) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "likelihood entry: bad arguments") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> dx, db;
+    BN_TRY(dx.bind(ctx, x, (size_t)n));
+    BN_TRY(db.bind(ctx, beta, (size_t)n));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, out, 1));
+    BN_LAUNCH(ctx, k_dense_gene, 1, 1024, 0, which, size, mu, dx.p, db.p, n, o.p);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+extern "C" int bn_marginal_nb_1d(bn_ctx *ctx, double SIZE, double MU, const double *m_observed, const double *BETA,
+                                 int64_t n, double *out)
+{
+    return dense_gene(ctx, 0, SIZE, MU, m_observed, BETA, n, out);
+}
+extern "C" int bn_marginal_nb_2d(bn_ctx *ctx, const double SIZE_MU[2], const double *m_observed, const double *BETA,
+                                 int64_t n, double *out)
+{
+    if (!SIZE_MU) return BN_ERR_INVALID;
+    return dense_gene(ctx, 0, SIZE_MU[0], SIZE_MU[1], m_observed, BETA, n, out);
+}
+extern "C" int bn_gradient_nb_1d(bn_ctx *ctx, double SIZE, double MU, const double *m_observed, const double *BETA,
+                                 int64_t n, double *out)
+{
+    return dense_gene(ctx, 1, SIZE, MU, m_observed, BETA, n, out);
+}
+extern "C" int bn_gradient_nb_2d(bn_ctx *ctx, const double SIZE_MU[2], const double *m_observed, const double *BETA,
+                                 int64_t n, double out[2])
+{
+    if (!SIZE_MU || !out) return BN_ERR_INVALID;
+    BN_TRY(dense_gene(ctx, 1, SIZE_MU[0], SIZE_MU[1], m_observed, BETA, n, out));
+    // out may be host or device; element 1 written by a second launch
+    return dense_gene(ctx, 2, SIZE_MU[0], SIZE_MU[1], m_observed, BETA, n, out + 1);
+}

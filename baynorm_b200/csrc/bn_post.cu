@@ -1,0 +1,345 @@
+// bn_post.cu -- the gene x cell posterior kernels (Main_mean_NB_Bay, Main_mode_NB_Bay,
+// Main_NB_Bay; src/bayNorm_main.cpp:1063-1299), binomial DownSampling (:892-915) and the
+// synthetic NB count generator the benchmarks use.
+//
+// Layout: a CTA owns a tile of TG = 2048 consecutive genes and walks NC consecutive cell
+// columns.  size/mu of the tile live in registers for the whole walk.  For every column the
+// CTA scatters that column's non-zeros (row indices are sorted, so the tile's slice is one
+// contiguous run found by binary search) into a shared-memory tile of counts, then every
+// thread evaluates the closed form for its genes and streams the result out: each output
+// element is written exactly once, 256 threads x 8 B contiguous per store instruction.
+// HBM traffic per element: 8 B written + 12 B * nnz-fraction read; beta/size/mu are
+// O(G + C) and stay in L2.
+//
+// Bit-exactness (mode): the reference's expression order is reproduced with explicit
+// round-to-nearest intrinsics, which the compiler never contracts into FMAs:
+//   tempmu = ((x + size) * (mu - mu*beta)) / (size + mu*beta)          (:1118, :1196, :1278)
+//   mode   = floor((tempmu / (size + x)) * ((size + x) - 1)) + x       (:1281), 0 if size+x <= 1
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "bn_internal.cuh"
+#include "bn_rng.cuh"
+
+#define POST_THREADS 256
+#define POST_EPT 8
+#define POST_TG (POST_THREADS * POST_EPT)
+
+enum { POST_MEAN = 0, POST_MODE = 1, POST_SAMPLE = 2 };
+
+__device__ __forceinline__ double post_tempmu(double x, double size, double mu, double beta)
+{
+    const double mb = __dmul_rn(mu, beta);
+    return __ddiv_rn(__dmul_rn(__dadd_rn(x, size), __dsub_rn(mu, mb)), __dadd_rn(size, mb));
+}
+
+// first index in [lo, hi) with rowidx[k] >= key
+__device__ __forceinline__ int64_t lower_bound_row(const int32_t *__restrict__ rowidx, int64_t lo, int64_t hi, int64_t key)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowidx + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(POST_THREADS)
+    k_posterior(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
+                const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
+                int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
+{
+    __shared__ double xs[2][POST_TG];
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * POST_TG;
+    double sz[POST_EPT], m[POST_EPT];
+#pragma unroll
+    for (int e = 0; e < POST_EPT; e++) {
+        const int64_t i = t0 + e * POST_THREADS + tid;
+        sz[e] = (i < G) ? __ldg(size + i) : 1.0;
+        m[e] = (i < G) ? __ldg(mu + i) : 0.0;
+    }
+    const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
+    const int64_t je = (jb + nc_per_cta < ncol) ? jb + nc_per_cta : ncol;
+    int buf = 0;
+    for (int64_t jj = jb; jj < je; jj++, buf ^= 1) {
+        const int64_t j = col0 + jj;
+        double *x = xs[buf];
+#pragma unroll
+        for (int e = 0; e < POST_EPT; e++) x[e * POST_THREADS + tid] = 0.0;
+        const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
+        const int64_t lo = lower_bound_row(rowidx, cs, ce, t0);
+        const int64_t hi = lower_bound_row(rowidx, lo, ce, t0 + POST_TG);
+        __syncthreads(); // zeros visible; also orders this buffer's previous readers (2 columns ago)
+        for (int64_t k = lo + tid; k < hi; k += POST_THREADS) x[__ldg(rowidx + k) - t0] = __ldcs(val + k);
+        __syncthreads();
+        const double b = __ldg(beta + j);
+        double *o = out + G * jj;
+#pragma unroll
+        for (int e = 0; e < POST_EPT; e++) {
+            const int64_t i = t0 + e * POST_THREADS + tid;
+            if (i >= G) continue;
+            const double xv = x[e * POST_THREADS + tid];
+            const double tm = post_tempmu(xv, sz[e], m[e], b);
+            if (MODE == POST_MEAN) {
+                __stcs(o + i, __dadd_rn(tm, xv));
+            } else if (MODE == POST_MODE) {
+                const double r = __dadd_rn(sz[e], xv);
+                double res = 0.0;
+                if (r > 1.0) res = __dadd_rn(floor(__dmul_rn(__ddiv_rn(tm, r), __dsub_rn(r, 1.0))), xv);
+                __stcs(o + i, res);
+            } else {
+                const double r = __dadd_rn(sz[e], xv);
+                const NBParams P = bn_nb_setup(r, tm);
+                Philox g;
+                g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
+                // one Philox counter block per 4 draws; sub-stream index = s / 4 so that the value
+                // of draw s does not depend on S
+                for (int s = 0; s < S; s++) {
+                    if ((s & 3) == 0) {
+                        g.c2 = (uint32_t)(s >> 2);
+                        g.c3 = 0;
+                        g.have = 0;
+                    }
+                    __stcs(o + i + sstride * s, bn_nb_draw(P, g) + xv);
+                }
+            }
+        }
+    }
+}
+
+static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BETA_vec, const double *size,
+                       const double *mu, int64_t col0, int64_t ncol, int S, uint64_t seed, double *out)
+{
+    if (!ctx || !m || !BETA_vec || !size || !mu || !out)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "posterior: NULL argument (mu is required: the NB model has no default)") : BN_ERR_INVALID;
+    if (col0 < 0 || ncol <= 0 || col0 + ncol > m->C) return bn_fail(ctx, BN_ERR_INVALID, "posterior: column block [%lld,+%lld) outside 0..%lld", (long long)col0, (long long)ncol, (long long)m->C);
+    if (mode == POST_SAMPLE && S <= 0) return bn_fail(ctx, BN_ERR_INVALID, "posterior: S must be positive");
+    cudaSetDevice(ctx->device);
+    const size_t nout = (size_t)m->G * (size_t)ncol * (size_t)(mode == POST_SAMPLE ? S : 1);
+    DevIn<double> b, sz, mm;
+    BN_TRY(b.bind(ctx, BETA_vec, (size_t)m->C));
+    BN_TRY(sz.bind(ctx, size, (size_t)m->G));
+    BN_TRY(mm.bind(ctx, mu, (size_t)m->G));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, out, nout));
+    const int64_t tiles = (m->G + POST_TG - 1) / POST_TG;
+    // enough CTAs to fill 148 SMs a few times over, but long enough column walks to amortise
+    // the size/mu register loads
+    int nc = 16;
+    while (nc > 1 && tiles * ((ncol + nc - 1) / nc) < 148 * 8) nc >>= 1;
+    const int64_t gy = (ncol + nc - 1) / nc;
+    if (gy > 65535) nc = (int)((ncol + 65534) / 65535);
+    dim3 grid((unsigned)tiles, (unsigned)((ncol + nc - 1) / nc));
+    const int64_t sstride = m->G * ncol;
+    if (mode == POST_MEAN)
+        BN_LAUNCH(ctx, k_posterior<POST_MEAN>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
+    else if (mode == POST_MODE)
+        BN_LAUNCH(ctx, k_posterior<POST_MODE>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
+    else
+        BN_LAUNCH(ctx, k_posterior<POST_SAMPLE>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+extern "C" int bn_post_mean(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                            int64_t col0, int64_t ncol, double *out)
+{
+    return post_launch(ctx, POST_MEAN, m, BETA_vec, size, mu, col0, ncol, 1, 0, out);
+}
+extern "C" int bn_post_mode(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                            int64_t col0, int64_t ncol, double *out)
+{
+    return post_launch(ctx, POST_MODE, m, BETA_vec, size, mu, col0, ncol, 1, 0, out);
+}
+extern "C" int bn_post_sample(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                              int64_t col0, int64_t ncol, int S, uint64_t seed, double *out)
+{
+    return post_launch(ctx, POST_SAMPLE, m, BETA_vec, size, mu, col0, ncol, S, seed, out);
+}
+
+// ---------------------------------------------------------------------------------
+// DownSampling: dense column-major in/out, one binomial draw per element, 16 B/element.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_downsample(int64_t G, int64_t C, const double *__restrict__ in,
+                                                    const double *__restrict__ beta, uint64_t seed,
+                                                    double *__restrict__ out)
+{
+    const int64_t total = G * C;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += gridDim.x * (int64_t)blockDim.x) {
+        const double n = __ldcs(in + e);
+        double r = 0.0;
+        if (n > 0.0) {
+            const int64_t j = e / G, i = e - j * G;
+            Philox g;
+            g.init(seed, (uint64_t)i + (uint64_t)j * 0x100000000ULL, 0x44533031u /* "DS01" */);
+            r = bn_rbinom(g, n, __ldg(beta + j));
+        }
+        __stcs(out + e, r);
+    }
+}
+
+extern "C" int bn_downsample(bn_ctx *ctx, int64_t G, int64_t C, const double *Data, const double *BETA_vec,
+                             uint64_t seed, double *out)
+{
+    if (!ctx || !Data || !BETA_vec || !out || G <= 0 || C <= 0)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_downsample: bad arguments") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> a, b;
+    BN_TRY(a.bind(ctx, Data, (size_t)G * C));
+    BN_TRY(b.bind(ctx, BETA_vec, (size_t)C));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, out, (size_t)G * C));
+    const int64_t want = (G * C + 255) / 256;
+    const int grid = (int)std::min<int64_t>(want, 148 * 32);
+    BN_LAUNCH(ctx, k_downsample, grid, 256, 0, G, C, a.p, b.p, seed, o.p);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------
+// synthetic counts: x_ij ~ NB(size phi_i, mean mu_i beta_j), written straight to CSC.
+// Two passes with the same counter-based draws: count per column, scan, fill in row order.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double synth_draw(int64_t gi, int64_t j, double phi, double mu, double beta, uint64_t seed)
+{
+    const double M = mu * beta;
+    const NBParams P = bn_nb_setup(phi, M);
+    Philox g;
+    g.init(seed, (uint64_t)gi + (uint64_t)j * 0x100000000ULL, 0x53594e30u /* "SYN0" */);
+    return bn_nb_draw(P, g);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_synth(int64_t G, int64_t C, const double *__restrict__ mu,
+                                               const double *__restrict__ size, const double *__restrict__ beta,
+                                               uint64_t seed, int64_t gene0, int64_t *__restrict__ cnt,
+                                               const int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
+                                               double *__restrict__ val)
+{
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    for (int64_t j = blockIdx.x; j < C; j += gridDim.x) {
+        const double b = beta[j];
+        int64_t base = FILL ? colptr[j] : 0;
+        int total = 0;
+        for (int64_t i0 = 0; i0 < G; i0 += 256) {
+            const int64_t i = i0 + threadIdx.x;
+            double x = 0.0;
+            if (i < G) x = synth_draw(gene0 + i, j, size[i], mu[i], b, seed);
+            const int f = (x > 0.0);
+            if (FILL) {
+                int pos, agg;
+                Scan(tmp).ExclusiveSum(f, pos, agg);
+                if (f) {
+                    rowidx[base + pos] = (int32_t)i;
+                    val[base + pos] = x;
+                }
+                base += agg;
+                __syncthreads();
+            } else
+                total += f;
+        }
+        if (!FILL) {
+            int incl;
+            Scan(tmp).InclusiveSum(total, incl);
+            if (threadIdx.x == 255) cnt[j] = incl;
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int bn_mat_synth_nb(bn_ctx *ctx, int64_t G, int64_t C, const double *mu, const double *size,
+                               const double *beta, uint64_t seed, int64_t gene0, bn_mat **out)
+{
+    if (!ctx || !out || !mu || !size || !beta || G <= 0 || C <= 0)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_mat_synth_nb: bad arguments") : BN_ERR_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    DevIn<double> dmu, dsz, db;
+    BN_TRY(dmu.bind(ctx, mu, (size_t)G));
+    BN_TRY(dsz.bind(ctx, size, (size_t)G));
+    BN_TRY(db.bind(ctx, beta, (size_t)C));
+    bn_mat *m = new bn_mat();
+    m->ctx = ctx;
+    m->G = G;
+    m->C = C;
+    m->gene0 = gene0;
+    m->is_count = true;
+    auto fail = [&](int rc) {
+        bn_mat_free(m);
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&m->colptr, (size_t)(C + 1) * 8)) != cudaSuccess)
+        return fail(bn_fail(ctx, BN_ERR_OOM, "colptr: %s", cudaGetErrorString(e)));
+    DevBuf<int64_t> cnt;
+    int rc = cnt.alloc(ctx, (size_t)C + 1);
+    if (rc) return fail(rc);
+    cudaMemsetAsync(cnt.p, 0, (size_t)(C + 1) * 8, ctx->stream);
+    const int grid = (int)std::min<int64_t>(C, 148 * 8);
+    k_synth<false><<<grid, 256, 0, ctx->stream>>>(G, C, dmu.p, dsz.p, db.p, seed, gene0, cnt.p, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, m->colptr, (int)(C + 1), ctx->stream);
+    DevBuf<char> tmp;
+    if ((rc = tmp.alloc(ctx, tb))) return fail(rc);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, m->colptr, (int)(C + 1), ctx->stream);
+    ctx->launches++;
+    int64_t nnz = 0;
+    if ((e = cudaMemcpyAsync(&nnz, m->colptr + C, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+        return fail(bn_fail(ctx, BN_ERR_CUDA, "synth scan: %s", cudaGetErrorString(e)));
+    if (nnz >= 4294967295LL) return fail(bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard"));
+    m->nnz = nnz;
+    if ((e = cudaMalloc((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8)) != cudaSuccess)
+        return fail(bn_fail(ctx, BN_ERR_OOM, "matrix allocation failed: %s", cudaGetErrorString(e)));
+    k_synth<true><<<grid, 256, 0, ctx->stream>>>(G, C, dmu.p, dsz.p, db.p, seed, gene0, nullptr, m->colptr, m->rowidx, m->val);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(bn_fail(ctx, BN_ERR_CUDA, "k_synth: %s", cudaGetErrorString(e)));
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+        return fail(bn_fail(ctx, BN_ERR_CUDA, "k_synth: %s", cudaGetErrorString(e)));
+    *out = m;
+    return BN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// debug hook: raw Philox4x32-10 block, so tests can pin the generator against the
+// published known-answer vectors (Random123 kat_vectors).
+// ---------------------------------------------------------------------------------
+__global__ void k_philox_block(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, uint32_t *__restrict__ out)
+{
+    Philox g;
+    g.k0 = key[0];
+    g.k1 = key[1];
+    g.c0 = ctr[0];
+    g.c1 = ctr[1];
+    g.c2 = ctr[2];
+    g.c3 = ctr[3];
+    g.have = 0;
+    g.refill();
+    out[0] = g.out[0];
+    out[1] = g.out[1];
+    out[2] = g.out[2];
+    out[3] = g.out[3];
+}
+
+extern "C" int bn_debug_philox(bn_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    if (!ctx || !ctr || !key || !out) return BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<uint32_t> c, k;
+    BN_TRY(c.bind(ctx, ctr, 4));
+    BN_TRY(k.bind(ctx, key, 2));
+    DevOut<uint32_t> o;
+    BN_TRY(o.bind(ctx, out, 4));
+    BN_LAUNCH(ctx, k_philox_block, 1, 1, 0, c.p, k.p, o.p);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}

@@ -1,0 +1,375 @@
+// bn_reduce.cu -- the reductions around the fit: library-size column sums and the
+// default BETA (R/bayNorm.r:164-170), method-of-moments prior (rowMeansFast / rowVarsFast
+// / EstPrior_sprcpp, src/bayNorm_main.cpp:1303-1394 with the x/beta normalisation of
+// R/PRIOR_FUNCTIONS.R:253 fused in), and AdjustSIZE_fun (R/sup_funs.R:27-33).
+//
+// All of these are HBM streams over the non-zeros (12 B per non-zero per pass) followed
+// by O(G) or O(C) epilogues; every reduction has a fixed order so results do not depend
+// on launch geometry, and cross-shard pieces go through bn_allreduce().
+#include <math.h>
+
+#include "bn_internal.cuh"
+
+// ---------------------------------------------------------------------------------
+// column sums: one warp per cell column, 8 columns per 256-thread CTA
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_colsums(int64_t C, const int64_t *__restrict__ colptr,
+                                                 const double *__restrict__ val, double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    for (int64_t j = warp; j < C; j += nwarp) {
+        const int64_t a = colptr[j], b = colptr[j + 1];
+        double s0 = 0.0, s1 = 0.0;
+        int64_t k = a + lane;
+        for (; k + 32 < b; k += 64) {
+            s0 += __ldcs(val + k);
+            s1 += __ldcs(val + k + 32);
+        }
+        if (k < b) s0 += __ldcs(val + k);
+        const double s = bn_warp_sum(s0 + s1);
+        if (lane == 0) out[j] = s;
+    }
+}
+
+extern "C" int bn_colsums(bn_ctx *ctx, const bn_mat *m, double *colsums)
+{
+    if (!ctx || !m || !colsums) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_colsums: NULL argument") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, colsums, (size_t)m->C));
+    const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
+    BN_LAUNCH(ctx, k_colsums, blocks, 256, 0, m->C, m->colptr, m->val, o.p);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------
+// one-CTA block reductions (fixed order: thread-strided partials, then a tree)
+// ---------------------------------------------------------------------------------
+enum { RED_SUM = 0, RED_MIN = 1, RED_MAX = 2 };
+
+template <int OP> __device__ __forceinline__ double red_op(double a, double b)
+{
+    return OP == RED_SUM ? a + b : (OP == RED_MIN ? fmin(a, b) : fmax(a, b));
+}
+template <int OP> __device__ double block_reduce_1024(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = red_op<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = sh[0];
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) r = red_op<OP>(r, sh[k]);
+    return r;
+}
+
+// beta = xx/mean(xx)*mean_beta; beta<=0 -> min positive; beta>=1 -> max below 1
+// (R/bayNorm.r:166-169).  status[0] = 1 when the range check of :185-187 fails.
+__global__ void __launch_bounds__(1024) k_beta_from_colsums(int64_t C, const double *__restrict__ xx, double mean_beta,
+                                                            double *__restrict__ beta, int *__restrict__ status)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < C; j += blockDim.x) s += xx[j];
+    const double mean = block_reduce_1024<RED_SUM>(s, sh) / (double)C;
+    double mn = INFINITY;
+    for (int64_t j = threadIdx.x; j < C; j += blockDim.x) {
+        const double b = __dmul_rn(__ddiv_rn(xx[j], mean), mean_beta);
+        beta[j] = b;
+        if (b > 0.0) mn = fmin(mn, b);
+    }
+    const double minpos = block_reduce_1024<RED_MIN>(mn, sh);
+    double mx = -INFINITY;
+    for (int64_t j = threadIdx.x; j < C; j += blockDim.x) {
+        double b = beta[j];
+        if (b <= 0.0) {
+            b = minpos;
+            beta[j] = b;
+        }
+        if (b < 1.0) mx = fmax(mx, b);
+    }
+    const double maxlt1 = block_reduce_1024<RED_MAX>(mx, sh);
+    double lo = INFINITY, hi = -INFINITY;
+    int nan = 0;
+    for (int64_t j = threadIdx.x; j < C; j += blockDim.x) {
+        double b = beta[j];
+        if (b >= 1.0) {
+            b = maxlt1;
+            beta[j] = b;
+        }
+        if (b != b) nan = 1;
+        lo = fmin(lo, b);
+        hi = fmax(hi, b);
+    }
+    lo = block_reduce_1024<RED_MIN>(lo, sh);
+    hi = block_reduce_1024<RED_MAX>(hi, sh);
+    nan = __syncthreads_or(nan);
+    if (threadIdx.x == 0) status[0] = (nan || !(lo > 0.0) || !(hi < 1.0)) ? 1 : 0;
+}
+
+extern "C" int bn_beta_default(bn_ctx *ctx, const bn_mat *m, double mean_beta, double *beta)
+{
+    if (!ctx || !m || !beta) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_beta_default: NULL argument") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, beta, (size_t)m->C));
+    DevBuf<double> xx;
+    BN_TRY(xx.alloc(ctx, (size_t)m->C));
+    DevBuf<int> st;
+    BN_TRY(st.alloc(ctx, 1));
+    const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
+    BN_LAUNCH(ctx, k_colsums, blocks, 256, 0, m->C, m->colptr, m->val, xx.p);
+    BN_TRY(bn_allreduce(ctx, xx.p, m->C, 0)); // per-cell totals over gene shards
+    BN_LAUNCH(ctx, k_beta_from_colsums, 1, 1024, 0, m->C, xx.p, mean_beta, o.p, st.p);
+    int h = 0;
+    BN_CUDA(ctx, cudaMemcpyAsync(&h, st.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BN_TRY(o.commit(ctx));
+    BN_TRY(bn_sync(ctx));
+    if (h) return bn_fail(ctx, BN_ERR_BETA_RANGE, "The range of BETA must be within (0,1).");
+    return BN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// per-gene moments on the gene-major twin: one warp per gene.
+// mode 0: full EstPrior (MU, SIZE with NaN rule, V)     -- means computed here
+// mode 1: rowMeansFast only (MU)
+// mode 2: rowVarsFast with caller-supplied means (VARS = raw variance, /(C-1))
+// mode 3: as mode 0 but SIZE is the raw quotient m^2/(v-m) without the R-level NaN rule
+//         (what EstPrior_sprcpp / EstPrior_rcpp themselves return)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_t C, const int64_t *__restrict__ rowptr,
+                                                     const int32_t *__restrict__ cell, const double *__restrict__ rval,
+                                                     const double *__restrict__ beta, const double *__restrict__ means_in,
+                                                     double *__restrict__ MU, double *__restrict__ SIZE,
+                                                     double *__restrict__ V)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    const double n = (double)C;
+    for (int64_t g = warp; g < G; g += nwarp) {
+        const int64_t a = rowptr[g], b = rowptr[g + 1];
+        double mean;
+        if (mode == 2) {
+            mean = means_in[g];
+        } else {
+            double s = 0.0;
+            for (int64_t k = a + lane; k < b; k += 32) {
+                const double x = rval[k];
+                s += beta ? __ddiv_rn(x, __ldg(beta + cell[k])) : x;
+            }
+            mean = __ddiv_rn(bn_warp_sum(s), n); // :1316-1318
+            if (lane == 0 && MU) MU[g] = mean;
+            if (mode == 1) continue;
+        }
+        double ss = 0.0;
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const double x = rval[k];
+            const double v = beta ? __ddiv_rn(x, __ldg(beta + cell[k])) : x;
+            const double d = __dsub_rn(v, mean);
+            ss = __dadd_rn(ss, __dmul_rn(d, d)); // :1331
+        }
+        ss = bn_warp_sum(ss);
+        if (lane == 0) {
+            const double nz = (double)(b - a);
+            double var = __dadd_rn(ss, __dmul_rn(__dsub_rn(n, nz), __dmul_rn(mean, mean))); // :1338
+            var = __ddiv_rn(var, (double)(C - 1));                                            // :1339
+            if (mode == 2) {
+                V[g] = var;
+            } else {
+                const double v = __dmul_rn(__ddiv_rn(__dsub_rn(n, 1.0), n), var);         // :1385
+                double size = __ddiv_rn(__dmul_rn(mean, mean), __dsub_rn(v, mean));       // :1386
+                if (mode == 0 && v <= mean) size = nan("");                               // R/PRIOR_FUNCTIONS.R:163
+                if (SIZE) SIZE[g] = size;
+                if (V) V[g] = v;
+            }
+        }
+    }
+}
+
+static int launch_row_moments(bn_ctx *ctx, bn_mat *m, int mode, const double *beta, const double *means_in, double *MU,
+                              double *SIZE, double *V)
+{
+    BN_TRY(bn_mat_ensure_csr(ctx, m));
+    const int blocks = (int)std::min<int64_t>((m->G + 7) / 8, 148 * 16);
+    BN_LAUNCH(ctx, k_row_moments, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->cell, m->rval, beta, means_in, MU, SIZE, V);
+    return BN_OK;
+}
+
+// device-pointer version used by bn_prior
+int bn_mme_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, double *d_MU, double *d_SIZE, double *d_V)
+{
+    return launch_row_moments(ctx, m, 0, d_beta, nullptr, d_MU, d_SIZE, d_V);
+}
+
+static int bn_mme_impl(bn_ctx *ctx, bn_mat *m, int mode, const double *beta, double *MU, double *SIZE, double *V)
+{
+    if (!ctx || !m) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_mme: NULL argument") : BN_ERR_INVALID;
+    if (m->C < 2) return bn_fail(ctx, BN_ERR_INVALID, "bn_mme needs at least 2 cells");
+    cudaSetDevice(ctx->device);
+    DevIn<double> b;
+    BN_TRY(b.bind(ctx, beta, (size_t)m->C));
+    DevOut<double> oMU, oS, oV;
+    BN_TRY(oMU.bind(ctx, MU, (size_t)m->G));
+    BN_TRY(oS.bind(ctx, SIZE, (size_t)m->G));
+    BN_TRY(oV.bind(ctx, V, (size_t)m->G));
+    BN_TRY(launch_row_moments(ctx, m, mode, b.p, nullptr, oMU.p, oS.p, oV.p));
+    BN_TRY(oMU.commit(ctx));
+    BN_TRY(oS.commit(ctx));
+    BN_TRY(oV.commit(ctx));
+    return bn_sync(ctx);
+}
+
+extern "C" int bn_mme(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, double *SIZE, double *V)
+{
+    return bn_mme_impl(ctx, m, 0, beta, MU, SIZE, V);
+}
+
+extern "C" int bn_row_means(bn_ctx *ctx, bn_mat *m, double *means)
+{
+    if (!ctx || !m || !means) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_row_means: NULL argument") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, means, (size_t)m->G));
+    BN_TRY(launch_row_moments(ctx, m, 1, nullptr, nullptr, o.p, nullptr, nullptr));
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+extern "C" int bn_row_vars(bn_ctx *ctx, bn_mat *m, const double *means, double *vars)
+{
+    if (!ctx || !m || !means || !vars) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_row_vars: NULL argument") : BN_ERR_INVALID;
+    if (m->C < 2) return bn_fail(ctx, BN_ERR_INVALID, "bn_row_vars needs at least 2 cells");
+    cudaSetDevice(ctx->device);
+    DevIn<double> mi;
+    BN_TRY(mi.bind(ctx, means, (size_t)m->G));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, vars, (size_t)m->G));
+    BN_TRY(launch_row_moments(ctx, m, 2, nullptr, mi.p, nullptr, nullptr, o.p));
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+extern "C" int bn_mme_dense(bn_ctx *ctx, int64_t G, int64_t C, const double *dense, double *MU, double *SIZE, double *V)
+{
+    if (!ctx) return BN_ERR_INVALID;
+    bn_mat *m = nullptr;
+    BN_TRY(bn_mat_from_dense(ctx, G, C, dense, &m));
+    // EstPrior_rcpp returns pow(m,2)/(v-m) as is; the NaN rule lives in R's EstPrior only.
+    int rc = bn_mme_impl(ctx, m, 3, nullptr, MU, SIZE, V);
+    bn_mat_free(m);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// cross-gene statistics (single CTA; G is tens of thousands)
+// ---------------------------------------------------------------------------------
+// out[0] = min over non-NaN v, out[1] = -max over non-NaN v   (so one min-all-reduce serves both)
+__global__ void __launch_bounds__(1024) k_minmax_nonan(int64_t n, const double *__restrict__ v, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double mn = INFINITY, mx = -INFINITY;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const double x = v[k];
+        if (x == x) {
+            mn = fmin(mn, x);
+            mx = fmax(mx, x);
+        }
+    }
+    mn = block_reduce_1024<RED_MIN>(mn, sh);
+    mx = block_reduce_1024<RED_MAX>(mx, sh);
+    if (threadIdx.x == 0) {
+        out[0] = mn;
+        out[1] = -mx;
+    }
+}
+
+// size_est[is.na(size_est)] <- min(size_est[!is.na(size_est)])   R/PRIOR_FUNCTIONS.R:259
+__global__ void k_fill_nan(int64_t n, double *__restrict__ v, const double *__restrict__ mm)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n && v[k] != v[k]) v[k] = mm[0];
+}
+
+// sums over genes with min < BB < max of {1, x, y, xx, xy}, x = log MME_SIZE, y = log BB
+__global__ void __launch_bounds__(1024) k_ols_sums(int64_t n, const double *__restrict__ bb, const double *__restrict__ ms,
+                                                   const double *__restrict__ mm, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    const double mn = mm[0], mx = -mm[1];
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const double b = bb[k];
+        if (b < mx && b > mn) {
+            const double x = log(ms[k]), y = log(b);
+            s[0] += 1.0;
+            s[1] += x;
+            s[2] += y;
+            s[3] += x * x;
+            s[4] += x * y;
+        }
+    }
+    for (int q = 0; q < 5; q++) {
+        const double r = block_reduce_1024<RED_SUM>(s[q], sh);
+        if (threadIdx.x == 0) out[q] = r;
+    }
+}
+
+// coefficients from the five sums, then exp(a + b log MME_SIZE) for every gene
+__global__ void k_adjust_apply(int64_t n, const double *__restrict__ ms, const double *__restrict__ sums,
+                               double *__restrict__ out, double *__restrict__ coef)
+{
+    const double N = sums[0], sx = sums[1], sy = sums[2], sxx = sums[3], sxy = sums[4];
+    const double mxv = sx / N, myv = sy / N;
+    const double b = (sxy - N * mxv * myv) / (sxx - N * mxv * mxv);
+    const double a = myv - b * mxv;
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = exp(a + b * log(ms[k]));
+    if (k == 0 && coef) {
+        coef[0] = a;
+        coef[1] = b;
+        coef[2] = N;
+    }
+}
+
+int bn_size_bounds_device(bn_ctx *ctx, int64_t G, double *d_size, double *d_mm /*[2]*/)
+{
+    BN_LAUNCH(ctx, k_minmax_nonan, 1, 1024, 0, G, d_size, d_mm);
+    BN_TRY(bn_allreduce(ctx, d_mm, 2, 1));
+    BN_LAUNCH(ctx, k_fill_nan, (unsigned)((G + 255) / 256), 256, 0, G, d_size, d_mm);
+    return BN_OK;
+}
+
+int bn_adjust_size_device(bn_ctx *ctx, int64_t G, const double *d_bb, const double *d_ms, double *d_out, double *d_coef)
+{
+    DevBuf<double> st;
+    BN_TRY(st.alloc(ctx, 8));
+    BN_LAUNCH(ctx, k_minmax_nonan, 1, 1024, 0, G, d_bb, st.p);
+    BN_TRY(bn_allreduce(ctx, st.p, 2, 1));
+    BN_LAUNCH(ctx, k_ols_sums, 1, 1024, 0, G, d_bb, d_ms, st.p, st.p + 2);
+    BN_TRY(bn_allreduce(ctx, st.p + 2, 5, 0));
+    BN_LAUNCH(ctx, k_adjust_apply, (unsigned)((G + 255) / 256), 256, 0, G, d_ms, st.p + 2, d_out, d_coef);
+    return BN_OK;
+}
+
+extern "C" int bn_adjust_size(bn_ctx *ctx, int64_t G, const double *BB_SIZE, const double *MME_SIZE, double *out,
+                              double coef[3])
+{
+    if (!ctx || !BB_SIZE || !MME_SIZE || !out || G <= 0)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_adjust_size: bad arguments") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> bb, ms;
+    BN_TRY(bb.bind(ctx, BB_SIZE, (size_t)G));
+    BN_TRY(ms.bind(ctx, MME_SIZE, (size_t)G));
+    DevOut<double> o, c;
+    BN_TRY(o.bind(ctx, out, (size_t)G));
+    BN_TRY(c.bind(ctx, coef, 3));
+    BN_TRY(bn_adjust_size_device(ctx, G, bb.p, ms.p, o.p, c.p));
+    BN_TRY(o.commit(ctx));
+    BN_TRY(c.commit(ctx));
+    return bn_sync(ctx);
+}

@@ -1,0 +1,201 @@
+// bn_rng.cuh -- counter-based Philox4x32-10 and the discrete samplers built on it.
+//
+// The reference draws from R's global Mersenne-Twister in loop order
+// (src/bayNorm_main.cpp:1121, :907); those streams cannot be reproduced on a GPU, so the
+// contract (BASELINE.json north_star) is distributional parity.  What this file guarantees
+// instead: the value of draw (gene, cell, s) is a pure function of (seed, global gene index,
+// global cell index, s), independent of tiling, sharding and GPU count.
+#pragma once
+#include <stdint.h>
+
+struct Philox {
+    uint32_t k0, k1;         // key  = seed
+    uint32_t c0, c1, c2, c3; // counter: (element lo, element hi, sample/sub-stream, refill index)
+    uint32_t out[4];
+    int have;
+
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t element, uint32_t substream)
+    {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32);
+        c0 = (uint32_t)element;
+        c1 = (uint32_t)(element >> 32);
+        c2 = substream;
+        c3 = 0;
+        have = 0;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, x0 = k0, x1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, a0), lo0 = 0xD2511F53u * a0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, a2), lo1 = 0xCD9E8D57u * a2;
+            const uint32_t n0 = hi1 ^ a1 ^ x0, n2 = hi0 ^ a3 ^ x1;
+            a0 = n0;
+            a1 = lo1;
+            a2 = n2;
+            a3 = lo0;
+            x0 += 0x9E3779B9u;
+            x1 += 0xBB67AE85u;
+        }
+        out[0] = a0;
+        out[1] = a1;
+        out[2] = a2;
+        out[3] = a3;
+        c3++;
+        have = 4;
+    }
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (have == 0) refill();
+        have--;
+        // select without dynamic register indexing
+        return have == 3 ? out[0] : (have == 2 ? out[1] : (have == 1 ? out[2] : out[3]));
+    }
+    // uniform on (0,1), 32 random bits, never 0 or 1
+    __device__ __forceinline__ double u32() { return ((double)next() + 0.5) * 2.3283064365386963e-10; }
+    // uniform on (0,1) with 53 random bits
+    __device__ __forceinline__ double u53()
+    {
+        const uint32_t a = next(), b = next();
+        const uint64_t v = (((uint64_t)a << 32) | b) >> 11;
+        return ((double)v + 0.5) * 1.1102230246251565e-16;
+    }
+};
+
+// ---- continuous helpers ---------------------------------------------------------------
+__device__ __forceinline__ double bn_rnorm(Philox &g)
+{ // Box-Muller, one value per call (the sine branch is dropped)
+    const double u = g.u53(), v = g.u32();
+    return sqrt(-2.0 * log(u)) * cospi(2.0 * v);
+}
+
+// Gamma(shape a, scale 1), Marsaglia & Tsang (2000); a < 1 boosted by U^(1/a).
+__device__ double bn_rgamma(Philox &g, double a)
+{
+    double boost = 1.0;
+    if (a < 1.0) {
+        boost = pow(g.u53(), 1.0 / a);
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = rsqrt(9.0 * d);
+    for (int it = 0; it < 64; it++) {
+        double x, v;
+        do {
+            x = bn_rnorm(g);
+            v = 1.0 + c * x;
+        } while (v <= 0.0);
+        v = v * v * v;
+        const double u = g.u53();
+        const double x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2) return d * v * boost;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return d * v * boost;
+    }
+    return d * boost; // unreachable in practice (acceptance > 95 % per round)
+}
+
+// Poisson(lam): sequential inversion below 10, Hoermann's PTRS (1993) above.
+__device__ double bn_rpois(Philox &g, double lam)
+{
+    if (!(lam > 0.0)) return 0.0;
+    if (lam < 10.0) {
+        double p = exp(-lam), u = g.u53(), k = 0.0;
+        while (u > p && k < 200.0) {
+            u -= p;
+            k += 1.0;
+            p *= lam / k;
+        }
+        return k;
+    }
+    const double slam = sqrt(lam), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0), ll = log(lam);
+    for (int it = 0; it < 256; it++) {
+        const double U = g.u53() - 0.5, V = g.u53(), us = 0.5 - fabs(U);
+        const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * ll - lgamma(k + 1.0)) return k;
+    }
+    return floor(lam);
+}
+
+// ---- negative binomial, size r > 0, mean M >= 0 -------------------------------------------
+// Small means (the vast majority of gene x cell entries: x = 0 and mu*beta << 1) are drawn
+// by CDF inversion from ONE uniform, starting from P(0) = (r/(r+M))^r; large means fall back
+// to the gamma-Poisson mixture the reference uses (rnbinom_mu == rpois(rgamma(size, mu/size))).
+struct NBParams {
+    double r, M, q, p0; // q = M/(r+M); p0 = P(0)
+    bool inversion;
+};
+#define BN_NB_INVERSION_MAX_MEAN 12.0
+
+__device__ __forceinline__ NBParams bn_nb_setup(double r, double M)
+{
+    NBParams P;
+    P.r = r;
+    P.M = M;
+    P.q = M / (r + M);
+    P.inversion = (M < BN_NB_INVERSION_MAX_MEAN);
+    P.p0 = P.inversion ? exp(-r * log1p(M / r)) : 0.0;
+    return P;
+}
+
+__device__ __forceinline__ double bn_nb_draw(const NBParams &P, Philox &g)
+{
+    if (!(P.M > 0.0)) return 0.0; // rgamma(shape, scale = 0) = 0 -> rpois(0) = 0
+    if (P.inversion) {
+        double u = g.u32(), p = P.p0, k = 0.0;
+        // p(k+1) = p(k) * q * (r + k) / (k + 1)
+        while (u > p && k < 4096.0) {
+            u -= p;
+            p *= P.q * (P.r + k) / (k + 1.0);
+            k += 1.0;
+        }
+        return k;
+    }
+    const double lam = bn_rgamma(g, P.r) * (P.M / P.r);
+    return bn_rpois(g, lam);
+}
+
+// ---- binomial(n, p) for DownSampling ----------------------------------------------------------
+// Inversion from 0 for n*min(p,1-p) < 30 (counts are small and beta ~ 0.06), Hoermann's BTRS above.
+__device__ double bn_rbinom(Philox &g, double n, double pp)
+{
+    if (!(n > 0.0) || !(pp > 0.0)) return 0.0;
+    if (pp >= 1.0) return n;
+    const bool flip = pp > 0.5;
+    const double p = flip ? 1.0 - pp : pp, q = 1.0 - p;
+    double k;
+    if (n * p < 30.0) {
+        const double s = p / q;
+        double f = exp(n * log1p(-p)), u = g.u53();
+        k = 0.0;
+        while (u > f && k < n) {
+            u -= f;
+            k += 1.0;
+            f *= s * (n - k + 1.0) / k;
+        }
+    } else {
+        const double spq = sqrt(n * p * q), b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * p;
+        const double c = n * p + 0.5, vr = 0.92 - 4.2 / b, alpha = (2.83 + 5.1 / b) * spq;
+        const double lpq = log(p / q), m = floor((n + 1.0) * p), h = lgamma(m + 1.0) + lgamma(n - m + 1.0);
+        k = m;
+        for (int it = 0; it < 256; it++) {
+            const double U = g.u53() - 0.5, us = 0.5 - fabs(U);
+            double V = g.u53();
+            const double kk = floor((2.0 * a / us + b) * U + c);
+            if (kk < 0.0 || kk > n) continue;
+            if (us >= 0.07 && V <= vr) {
+                k = kk;
+                break;
+            }
+            V = log(V * alpha / (a / (us * us) + b));
+            if (V <= h - lgamma(kk + 1.0) - lgamma(n - kk + 1.0) + (kk - m) * lpq) {
+                k = kk;
+                break;
+            }
+        }
+    }
+    return flip ? n - k : k;
+}

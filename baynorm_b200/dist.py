@@ -1,0 +1,92 @@
+"""Gene-sharded multi-GPU plumbing.
+
+One process per GPU.  Rank k owns a block of genes (rows) of the matrix and every per-gene
+stage runs shard-local.  The only exchanges are
+  * one sum all-reduce of the per-cell column totals (default BETA, R/bayNorm.r:166), C doubles;
+  * per prior set: min/max of the MME sizes (R/PRIOR_FUNCTIONS.R:259, :277-279), min/max of
+    BB_SIZE and the five OLS sums of AdjustSIZE_fun (R/sup_funs.R:28-30): <= 7 doubles each.
+The C library asks for them through the all-reduce hook (bn_ctx_set_allreduce); this module
+provides the hook on top of torch.distributed (NCCL on GPUs, gloo in the CPU tests) plus the
+host-side partitioning helpers.  The reference has no counterpart: its only parallelism is a
+SOCK cluster over genes (R/PRIOR_FUNCTIONS.R:426-427) that ships the whole matrix to every
+worker.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+_OPS = {0: "SUM", 1: "MIN", 2: "MAX"}
+
+
+def balanced_gene_blocks(row_nnz, world, n_cells=0):
+    """Contiguous gene blocks with near-equal cost.  Fit cost per gene ~ n_cells (dense zero
+    term) + c * nnz_gene, posterior cost ~ n_cells; expression is heavy-tailed, so blocks are
+    balanced on (n_cells + 4 * nnz_gene) instead of on gene count.  Returns world+1 boundaries."""
+    row_nnz = np.asarray(row_nnz, dtype=np.float64)
+    G = row_nnz.shape[0]
+    if world <= 1:
+        return np.array([0, G], dtype=np.int64)
+    cost = np.cumsum(float(n_cells) + 4.0 * row_nnz)
+    total = cost[-1]
+    bounds = [0]
+    for k in range(1, world):
+        b = int(np.searchsorted(cost, total * k / world, side="left")) + 1
+        b = max(b, bounds[-1] + 1)          # every rank gets at least one gene
+        b = min(b, G - (world - k))
+        bounds.append(b)
+    bounds.append(G)
+    return np.array(bounds, dtype=np.int64)
+
+
+def split_csc_rows(G, Cn, p, i, x, g0, g1):
+    """Rows [g0, g1) of a CSC matrix as a new CSC (row indices rebased to the block).  Row indices
+    are sorted within a column, so each column contributes one contiguous run."""
+    p = np.asarray(p, dtype=np.int64)
+    i = np.asarray(i)
+    keep = (i >= g0) & (i < g1)
+    csum = np.concatenate([[0], np.cumsum(keep, dtype=np.int64)])
+    newp = csum[p]
+    return g1 - g0, Cn, newp.astype(np.int64), (i[keep] - g0).astype(np.int32), np.asarray(x)[keep]
+
+
+class _CudaBuf:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def make_allreduce_hook(group=None, device=None):
+    """Returns fn(buf_ptr, count, dtype, op, stream_ptr) -> 0 running torch.distributed.all_reduce in
+    place on the memory at buf_ptr.  Device pointers (device is a torch cuda device) are aliased
+    through __cuda_array_interface__ and the collective is enqueued on the library's own stream;
+    host pointers (device None: gloo tests) are aliased through numpy."""
+    import torch
+    import torch.distributed as td
+
+    def hook(buf, count, dtype, op, stream):
+        if dtype != 0:
+            return 2
+        rop = getattr(td.ReduceOp, _OPS[op])
+        if device is not None and torch.device(device).type == "cuda":
+            t = torch.as_tensor(_CudaBuf(buf, count), device=device)
+            s = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.current_stream(device)
+            with torch.cuda.stream(s):
+                td.all_reduce(t, op=rop, group=group)
+            s.synchronize()
+        else:
+            arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(count,))
+            t = torch.from_numpy(arr)
+            td.all_reduce(t, op=rop, group=group)
+        return 0
+
+    return hook
+
+
+def install_torch_allreduce(ctx, rank, world, group=None):
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_allreduce(make_allreduce_hook(group, dev), rank, world)

@@ -1,0 +1,228 @@
+/*
+ * baynorm_b200.h -- C ABI of the B200-native bayNorm hot path.
+ *
+ * One shared library (libbaynorm_b200.so, sm_100a only) replaces the native layer
+ * of WT215/bayNorm (src/bayNorm_main.cpp, reached today through the 15 .Call
+ * routines registered at src/RcppExports.cpp:211-228) plus the R-level per-gene
+ * optimiser loop (BB_Fun, R/PRIOR_FUNCTIONS.R:380-549) and the prior orchestration
+ * (Prior_fun, R/PRIOR_FUNCTIONS.R:241-311).  Every entry point below names the
+ * reference interface it stands in for.  INTEGRATION.md shows the .Call shim a
+ * maintainer adds on the R side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no R, Rcpp, torch or CUDA types.
+ *  - Every data pointer may be HOST or DEVICE memory; the library inspects the
+ *    pointer (cudaPointerGetAttributes) and stages host buffers itself.  Pinned
+ *    host memory is copied at PCIe rate, pageable memory more slowly.
+ *  - Dense matrices are column-major (R layout): element (gene i, cell j) of a
+ *    G x C matrix is at [i + G*j].  3-D output is the reference's arma::cube
+ *    layout dim=c(G,C,S): [i + G*(j + C*s)]  (src/bayNorm_main.cpp:1091,1123).
+ *  - Sparse input is dgCMatrix-style CSC: p[C+1] column pointers (int32 as in
+ *    R's @p, or int64 for > 2^31-1 non-zeros), i[nnz] 0-based int32 row indices
+ *    sorted within each column, x[nnz] double  (R/sup_funs.R:99-106).
+ *  - All entry points return 0 on success or a BN_ERR_* code; bn_last_error(ctx)
+ *    gives a message.  No exceptions, no longjmp, no R API calls.  There is no
+ *    CPU fallback: without a usable sm_100 device bn_ctx_create fails.
+ *  - A context is driven by one host thread at a time.  One context = one GPU;
+ *    multi-GPU runs use one process (or one context) per GPU, each holding a
+ *    gene block of the matrix, and exchange the few cross-shard quantities through
+ *    the all-reduce hook (bn_ctx_set_allreduce).
+ *  - The library never keeps a host pointer after a call returns.
+ */
+#ifndef BAYNORM_B200_H
+#define BAYNORM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BN_API __attribute__((visibility("default")))
+#else
+#define BN_API
+#endif
+
+#define BN_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes --------------------------------------------------------- */
+enum {
+    BN_OK = 0,
+    BN_ERR_INVALID = 1,   /* bad argument (NULL, negative size, unsorted rows, ...) */
+    BN_ERR_CUDA = 2,      /* CUDA runtime error; message has the cudaError string */
+    BN_ERR_NO_DEVICE = 3, /* no sm_100 GPU: there is no CPU fallback */
+    BN_ERR_OOM = 4,       /* device or host allocation failed */
+    BN_ERR_BETA_RANGE = 5,/* "The range of BETA must be within (0,1)." R/bayNorm.r:185-187 */
+    BN_ERR_NONCOUNT = 6,  /* likelihood fit needs non-negative integer counts (dnbinom_mu) */
+    BN_ERR_COLLECTIVE = 7,/* the all-reduce hook returned non-zero */
+    BN_ERR_UNSUPPORTED = 8
+};
+
+typedef struct bn_ctx bn_ctx; /* one GPU: stream, workspace, last error */
+typedef struct bn_mat bn_mat; /* device-resident gene x cell matrix (CSC + gene-major CSR built on demand) */
+
+/* ---- context --------------------------------------------------------------- */
+BN_API int bn_version(void);
+BN_API int bn_ctx_create(int device, bn_ctx **out);
+BN_API void bn_ctx_destroy(bn_ctx *ctx);
+BN_API const char *bn_last_error(const bn_ctx *ctx); /* ctx may be NULL: last creation error */
+BN_API int bn_ctx_synchronize(bn_ctx *ctx);
+/* Opaque cudaStream_t the context launches on (so callers can time it with events). */
+BN_API void *bn_ctx_stream(bn_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+BN_API int64_t bn_ctx_launch_count(const bn_ctx *ctx);
+/* Device properties the bench reports: out[0]=SM count, [1]=clock kHz, [2]=cc major*10+minor, [3]=total bytes */
+BN_API int bn_ctx_device_info(bn_ctx *ctx, int64_t out[4]);
+
+/* Cross-shard all-reduce hook.  dtype: 0 = float64.  op: 0 = sum, 1 = min, 2 = max.
+ * buf is DEVICE memory of `count` elements, reduced in place across all shards; the
+ * work must be ordered after everything already enqueued on `stream` (cudaStream_t)
+ * and complete (or be stream-ordered) before the hook returns.  With world == 1 (the
+ * default) the hook is never called.  Replaces nothing in the reference (its only
+ * parallelism is a SOCK cluster, R/PRIOR_FUNCTIONS.R:426-427); this is the one
+ * exchange step of the gene-sharded path. */
+typedef int (*bn_allreduce_fn)(void *user, void *buf, int64_t count, int dtype, int op, void *stream);
+BN_API int bn_ctx_set_allreduce(bn_ctx *ctx, bn_allreduce_fn fn, void *user, int rank, int world);
+
+/* ---- matrices ---------------------------------------------------------------- */
+/* dgCMatrix in.  p_is_int64: 0 -> p is int32[C+1] (R's @p), 1 -> int64[C+1].
+ * Stands in for `as<arma::sp_mat>(Data)` in every Main_* wrapper
+ * (src/RcppExports.cpp:76-90) -- but the copy lands in HBM once and is reused. */
+BN_API int bn_mat_from_csc(bn_ctx *ctx, int64_t G, int64_t C, const void *p, int p_is_int64, const int32_t *i,
+                           const double *x, bn_mat **out);
+/* Dense column-major double G x C in (what Check_input turns into a dgCMatrix at
+ * R/sup_funs.R:105); explicit zeros are dropped on the device. */
+BN_API int bn_mat_from_dense(bn_ctx *ctx, int64_t G, int64_t C, const double *dense, bn_mat **out);
+BN_API void bn_mat_free(bn_mat *m);
+/* out[0]=G, [1]=C, [2]=nnz, [3]=1 if all values are non-negative integers */
+BN_API int bn_mat_info(const bn_mat *m, int64_t out[4]);
+/* Position of this block inside the whole matrix (gene-sharded / column-blocked runs):
+ * gene0 = global index of local gene 0, cell0 likewise.  Only the RNG counters use it, so
+ * that sample (gene, cell, s) does not depend on how the matrix was split. */
+BN_API int bn_mat_set_origin(bn_mat *m, int64_t gene0, int64_t cell0);
+/* Copy the CSC arrays back (p as int64).  Any pointer may be NULL. */
+BN_API int bn_mat_export_csc(bn_ctx *ctx, const bn_mat *m, int64_t *p, int32_t *i, double *x);
+/* New matrix holding columns idx[0..n) of m (Data[, which(Conditions == level)],
+ * R/bayNorm.r:265-270). idx is host or device int64. */
+BN_API int bn_mat_select_cols(bn_ctx *ctx, const bn_mat *m, const int64_t *idx, int64_t n, bn_mat **out);
+/* Synthetic NB counts x_ij ~ NB(size phi_i, mean mu_i*beta_j) generated on the device
+ * straight into CSC (SURVEY.md 8(d) generator; bench/test input, not a reference API). */
+BN_API int bn_mat_synth_nb(bn_ctx *ctx, int64_t G, int64_t C, const double *mu, const double *size,
+                           const double *beta, uint64_t seed, int64_t gene0, bn_mat **out);
+
+/* ---- beta / library size  (R/bayNorm.r:164-170) ------------------------------ */
+/* colsums[C] = Matrix::colSums(Data) of this shard (no collective). */
+BN_API int bn_colsums(bn_ctx *ctx, const bn_mat *m, double *colsums);
+/* beta[C] = colsums/mean(colsums)*mean_beta with the two clamps, then the (0,1) range
+ * check (BN_ERR_BETA_RANGE).  Runs the all-reduce hook on the column sums when world > 1. */
+BN_API int bn_beta_default(bn_ctx *ctx, const bn_mat *m, double mean_beta, double *beta);
+
+/* ---- method-of-moments prior  (EstPrior_sprcpp, src/bayNorm_main.cpp:1370-1394;
+ *      rowMeansFast :1303, rowVarsFast :1323; NaN rule R/PRIOR_FUNCTIONS.R:163) ---- */
+/* beta may be NULL (data already normalised, as EstPrior_sprcpp is called upstream) or
+ * beta[C]: the x/beta normalisation of R/PRIOR_FUNCTIONS.R:253 is then fused in.
+ * MU[G], SIZE[G] (NaN where v <= m, i.e. after the rule at :163), V[G]; any may be NULL. */
+BN_API int bn_mme(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, double *SIZE, double *V);
+/* rowMeansFast / rowVarsFast as separate calls (registered .Call routines). */
+BN_API int bn_row_means(bn_ctx *ctx, bn_mat *m, double *means);
+BN_API int bn_row_vars(bn_ctx *ctx, bn_mat *m, const double *means, double *vars);
+/* EstPrior_rcpp (dense twin, src/bayNorm_main.cpp:1423-1449). */
+BN_API int bn_mme_dense(bn_ctx *ctx, int64_t G, int64_t C, const double *dense, double *MU, double *SIZE, double *V);
+
+/* ---- likelihood / gradient for one gene (registered .Call routines) ------------ */
+/* MarginalF_NB_1D(SIZE, MU, m_observed, BETA)  src/bayNorm_main.cpp:928-943 */
+BN_API int bn_marginal_nb_1d(bn_ctx *ctx, double SIZE, double MU, const double *m_observed, const double *BETA,
+                             int64_t n, double *out);
+/* MarginalF_NB_2D(SIZE_MU, m_observed, BETA)  :948-965 */
+BN_API int bn_marginal_nb_2d(bn_ctx *ctx, const double SIZE_MU[2], const double *m_observed, const double *BETA,
+                             int64_t n, double *out);
+/* GradientFun_NB_1D  :972-987 */
+BN_API int bn_gradient_nb_1d(bn_ctx *ctx, double SIZE, double MU, const double *m_observed, const double *BETA,
+                             int64_t n, double *out);
+/* GradientFun_NB_2D  :993-1013; out[2] = {d/dsize, d/dmu} */
+BN_API int bn_gradient_nb_2d(bn_ctx *ctx, const double SIZE_MU[2], const double *m_observed, const double *BETA,
+                             int64_t n, double out[2]);
+
+/* ---- per-gene maximum marginal likelihood (BB_Fun, R/PRIOR_FUNCTIONS.R:380-549) - */
+enum { BN_FIT_SPG = 0, BN_FIT_BRENT = 1 };
+typedef struct {
+    int32_t method;    /* BN_FIT_SPG: BB::spg restated (reference-faithful, default);
+                          BN_FIT_BRENT: bounded golden-section/parabolic argmax */
+    int32_t maxfeval;  /* 500  (R/PRIOR_FUNCTIONS.R:451-454) */
+    int32_t maxit;     /* 1500 (BB default) */
+    int32_t M;         /* 10   (BB default, nonmonotone window) */
+    double ftol;       /* 1e-10 */
+    double gtol;       /* 1e-5 */
+    double eps;        /* 1e-7 forward-difference step */
+    double xatol;      /* 1e-10 (Brent only) */
+    int32_t use_gradient; /* GR=TRUE: analytic GradientFun_NB_1D instead of differences */
+    int32_t reserved;
+} bn_fit_opts;
+BN_API void bn_fit_opts_default(bn_fit_opts *o);
+/* FIX_MU=TRUE fit of `size` for every gene of the shard: start INITIAL_SIZE_vec[G], mean
+ * INITIAL_MU_vec[G] fixed, box [SIZE_lower, SIZE_upper].  Outputs (any may be NULL):
+ * size_out[G] (BB_opt$par), conv[G] (spg convergence code), nfeval[G] (likelihood
+ * evaluations incl. finite differences).  `parallel`/`NCores` have no equivalent. */
+BN_API int bn_fit_size(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const double *INITIAL_MU_vec,
+                       const double *INITIAL_SIZE_vec, double SIZE_lower, double SIZE_upper, const bn_fit_opts *opts,
+                       double *size_out, int32_t *conv, int32_t *nfeval);
+
+/* ---- AdjustSIZE_fun  (R/sup_funs.R:27-33) --------------------------------------- */
+/* out[G] = exp(a + b*log(MME_SIZE)), (a,b) = OLS of log BB_SIZE on log MME_SIZE over genes
+ * strictly inside (min BB, max BB).  coef (may be NULL) receives {a, b, n_fit}.  Uses the
+ * all-reduce hook for min/max and the five sums when world > 1. */
+BN_API int bn_adjust_size(bn_ctx *ctx, int64_t G, const double *BB_SIZE, const double *MME_SIZE, double *out,
+                          double coef[3]);
+
+/* ---- Prior_fun  (R/PRIOR_FUNCTIONS.R:241-311), FIX_MU=TRUE ------------------------ */
+typedef struct {
+    double *MME_MU;          /* [G] */
+    double *MME_SIZE;        /* [G] NaN already replaced by the global min (:259) */
+    double *BB_SIZE;         /* [G] NULL unless BB_SIZE requested */
+    double *MME_SIZE_adjust; /* [G] NULL unless BB_SIZE requested */
+    int32_t *conv;           /* [G] optional */
+    int32_t *nfeval;         /* [G] optional */
+    double size_lower, size_upper; /* bounds handed to the fit (:277-279) */
+    double coef[3];          /* a, b, n_fit of AdjustSIZE_fun */
+    double seconds[4];       /* device time: MME, fit, adjust, total */
+} bn_prior_out;
+BN_API int bn_prior(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, int BB_SIZE, const bn_fit_opts *opts,
+                    bn_prior_out *out);
+
+/* ---- posterior  (Main_*_NB_Bay, src/bayNorm_main.cpp:1063-1299, :1519-1601) ------- */
+/* Columns [col0, col0+ncol) of the matrix; out is column-major G x ncol.  S/thres of the
+ * reference signature are unused by mean/mode upstream and have no parameter here. */
+BN_API int bn_post_mean(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                        int64_t col0, int64_t ncol, double *out);
+BN_API int bn_post_mode(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                        int64_t col0, int64_t ncol, double *out);
+/* S draws x + NB(size+x, tempmu) per gene x cell: out[i + G*(j + ncol*s)], j local to the
+ * block.  Pure function of (inputs, seed, matrix origin): Philox4x32-10 keyed by seed with
+ * the (global gene, global cell, s) triple as counter.  The R shim draws `seed` from R's RNG
+ * inside GetRNGstate/PutRNGstate so set.seed() keeps runs reproducible
+ * (tests/testthat/test-bayNorm.r:9-17). */
+BN_API int bn_post_sample(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                          int64_t col0, int64_t ncol, int S, uint64_t seed, double *out);
+
+/* ---- DownSampling  (src/bayNorm_main.cpp:892-915) ---------------------------------- */
+/* Dense column-major in/out; out[i,j] ~ Binomial(Data[i,j], BETA_vec[j]). */
+BN_API int bn_downsample(bn_ctx *ctx, int64_t G, int64_t C, const double *Data, const double *BETA_vec,
+                         uint64_t seed, double *out);
+
+/* ---- benchmarking helpers ---------------------------------------------------------- */
+/* Forget the gene-major twin of the matrix so the next per-gene stage rebuilds it (bench.py
+ * times the build inside every step). */
+BN_API int bn_mat_drop_gene_major(bn_mat *m);
+/* Measured FP64 FMA rate of the device in flop/s (roofline denominator of the fit kernel). */
+BN_API int bn_debug_fp64_peak(bn_ctx *ctx, double *flops_per_s);
+
+/* ---- debug ------------------------------------------------------------------------- */
+/* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
+ * generator against the published known-answer vectors. */
+BN_API int bn_debug_philox(bn_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYNORM_B200_H */
