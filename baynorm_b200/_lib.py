@@ -78,6 +78,7 @@ SIGNATURES = {
     "bn_post_sample": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, C.c_int, _U64, _VP]),
     "bn_downsample": (C.c_int, [_VP, _I64, _I64, _VP, _VP, _U64, _VP]),
     "bn_debug_philox": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "bn_debug_log": (C.c_int, [_VP, C.c_int, _VP, _I64, _VP]),
     "bn_mat_drop_gene_major": (C.c_int, [_VP]),
     "bn_debug_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
 }

@@ -20,6 +20,9 @@
 #include <math.h>
 
 #include "bn_internal.cuh"
+#include "bn_math.cuh"
+
+#define FIT_HMAX 64 // counts up to here go through the tail table, larger ones through Stirling
 
 struct FitGene {
     const int32_t *cell; // this gene's non-zeros
@@ -27,42 +30,61 @@ struct FitGene {
     int64_t nnz;
     const double *beta, *logbeta;
     int64_t C;
-    double mu, lmu, K; // K = sum lgamma(x+1)
+    double mu, lmu;
+    double Kc;             // sum x*log(mu*beta_j) - sum lgamma(x+1): does not depend on phi
+    double beta_max;
+    const uint32_t *tail;  // shared memory: tail[k] = #{non-zeros with x > k}, k < FIT_HMAX
+    int kmax;              // min(FIT_HMAX, largest count)
+    int n_big;             // non-zeros with x > FIT_HMAX
 };
 
-// lgamma(x+phi) - lgamma(phi) for integer x >= 1
-__device__ __forceinline__ double lgamma_delta(double x, double phi, double lgphi)
-{
-    if (x <= 8.0) {
-        double p = phi;
-        for (double k = 1.0; k < x; k += 1.0) p *= (phi + k);
-        return log(p);
-    }
-    return lgamma(x + phi) - lgphi;
-}
-
-template <int TPG> __device__ double nb_loglik(const FitGene &g, double phi, double *scratch, int tid)
+// -l is evaluated as
+//   l(phi) = -phi * sum_{all cells} log1p(m_j/phi)  -  sum_{nz} x_j log(phi + m_j)
+//            + sum_{k < kmax} tail_k log(phi + k)  +  sum_{x_j > HMAX} [lgamma(x_j+phi) - lgamma(HMAX+phi)]  +  Kc
+// using lgamma(x+phi) - lgamma(phi) = sum_{k<x} log(phi+k): all non-zeros of the gene share the
+// same 64 logarithms, so a non-zero costs ONE log per evaluation and a cell costs one log1p.
+template <int TPG>
+__device__ double nb_loglik(const FitGene &g, double phi, const BnLogEntry *__restrict__ tab, double *scratch, int tid)
 {
     const double r = g.mu / phi;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int64_t j = tid;
-    for (; j + 3 * TPG < g.C; j += 4 * TPG) {
-        a0 += log1p(r * __ldg(g.beta + j));
-        a1 += log1p(r * __ldg(g.beta + j + TPG));
-        a2 += log1p(r * __ldg(g.beta + j + 2 * TPG));
-        a3 += log1p(r * __ldg(g.beta + j + 3 * TPG));
+    if (r * g.beta_max <= 0.015625) {
+        for (; j + 3 * TPG < g.C; j += 4 * TPG) {
+            a0 += bn_log1p_small(r * __ldg(g.beta + j));
+            a1 += bn_log1p_small(r * __ldg(g.beta + j + TPG));
+            a2 += bn_log1p_small(r * __ldg(g.beta + j + 2 * TPG));
+            a3 += bn_log1p_small(r * __ldg(g.beta + j + 3 * TPG));
+        }
+        for (; j < g.C; j += TPG) a0 += bn_log1p_small(r * __ldg(g.beta + j));
+    } else {
+        for (; j + 3 * TPG < g.C; j += 4 * TPG) {
+            a0 += bn_log1p_pos(r * __ldg(g.beta + j), tab);
+            a1 += bn_log1p_pos(r * __ldg(g.beta + j + TPG), tab);
+            a2 += bn_log1p_pos(r * __ldg(g.beta + j + 2 * TPG), tab);
+            a3 += bn_log1p_pos(r * __ldg(g.beta + j + 3 * TPG), tab);
+        }
+        for (; j < g.C; j += TPG) a0 += bn_log1p_pos(r * __ldg(g.beta + j), tab);
     }
-    for (; j < g.C; j += TPG) a0 += log1p(r * __ldg(g.beta + j));
     double acc = -phi * ((a0 + a1) + (a2 + a3));
-    const double lgphi = lgamma(phi);
-    double sp = 0.0;
-    for (int64_t k = tid; k < g.nnz; k += TPG) {
-        const int32_t c = g.cell[k];
-        const double x = g.rval[k];
-        const double m = g.mu * __ldg(g.beta + c);
-        sp += x * ((g.lmu + __ldg(g.logbeta + c)) - log(phi + m)) + lgamma_delta(x, phi, lgphi);
+    double s0 = 0.0, s1 = 0.0;
+    int64_t k = tid;
+    if (g.n_big == 0) {
+        for (; k + TPG < g.nnz; k += 2 * TPG) {
+            s0 = fma(-g.rval[k], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
+            s1 = fma(-g.rval[k + TPG], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k + TPG]), phi), tab), s1);
+        }
+        for (; k < g.nnz; k += TPG) s0 = fma(-g.rval[k], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
+    } else {
+        const double lgref = bn_lgamma_stirling(phi + (double)FIT_HMAX, tab);
+        for (; k < g.nnz; k += TPG) {
+            const double x = g.rval[k];
+            s0 = fma(-x, bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
+            if (x > (double)FIT_HMAX) s1 += bn_lgamma_stirling(x + phi, tab) - lgref;
+        }
     }
-    return bn_group_sum<TPG>(acc + sp, scratch) - g.K;
+    for (int q = tid; q < g.kmax; q += TPG) s1 = fma((double)g.tail[q], bn_log(phi + (double)q, tab), s1);
+    return bn_group_sum<TPG>(acc + (s0 + s1), scratch) + g.Kc;
 }
 
 // d l / d phi = sum_j [ digamma(x+phi) - digamma(phi) + log(phi/(phi+m_j)) + (m_j - x)/(m_j + phi) ]
@@ -355,17 +377,31 @@ struct BrentState {
     }
 };
 
-template <int TPG>
-__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG)
+template <int TPG> __device__ __forceinline__ void group_sync()
+{
+    if (TPG == 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <int TPG, bool GRAD>
+__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
     k_fit_size(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ cell,
                const double *__restrict__ rval, const double *__restrict__ beta, const double *__restrict__ logbeta,
-               const double *__restrict__ mu0, const double *__restrict__ size0, double lower, double upper, FitOpts o,
-               unsigned long long *__restrict__ queue, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
-               int32_t *__restrict__ nfe_out)
+               const double *__restrict__ mu0, const double *__restrict__ size0, double lower, double upper,
+               double beta_max, FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
+               int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
 {
+    constexpr int NGROUP = (TPG == 32) ? 4 : 1;
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
     __shared__ double scratch[8];
     __shared__ unsigned long long next_gene;
+    __shared__ uint32_t hist_all[NGROUP][FIT_HMAX + 1];
+    __shared__ int xmax_all[NGROUP];
+    bn_log_table_load(tab);
+    __syncthreads();
     const int tid = (TPG == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int grp = (TPG == 32) ? (threadIdx.x >> 5) : 0;
+    uint32_t *hist = hist_all[grp];
     for (;;) {
         unsigned long long gq;
         if (TPG == 32) {
@@ -389,6 +425,8 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG)
         g.C = C;
         g.mu = mu0[gi];
         g.lmu = log(g.mu);
+        g.beta_max = beta_max;
+        g.tail = hist;
         double par = size0[gi], res = par;
         int conv = 0, nfe = 0;
         if (g.nnz == 0 || !(g.mu > 0.0)) {
@@ -396,15 +434,38 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG)
             res = proj(par, lower, upper);
             if (o.method == BN_FIT_SPG) nfe = 2;
         } else {
+            // per-gene constants: count histogram -> tail table, Kc, largest count
+            for (int q = tid; q <= FIT_HMAX; q += TPG) hist[q] = 0;
+            if (tid == 0) xmax_all[grp] = 0;
+            group_sync<TPG>();
             double kk = 0.0;
-            for (int64_t k = tid; k < g.nnz; k += TPG) kk += lgamma(g.rval[k] + 1.0);
-            g.K = bn_group_sum<TPG>(kk, scratch);
+            int xm = 0;
+            for (int64_t k = tid; k < g.nnz; k += TPG) {
+                const double x = g.rval[k];
+                kk += x * (g.lmu + __ldg(logbeta + g.cell[k])) - lgamma(x + 1.0);
+                const int xi = x > (double)FIT_HMAX ? FIT_HMAX + 1 : (int)x;
+                atomicAdd(&hist[xi - 1], 1u);
+                xm = max(xm, xi);
+            }
+            atomicMax(&xmax_all[grp], xm);
+            g.Kc = bn_group_sum<TPG>(kk, scratch);
+            group_sync<TPG>();
+            if (tid == 0) { // suffix sum: tail[k] = #{x > k}
+                uint32_t run = hist[FIT_HMAX];
+                for (int q = FIT_HMAX - 1; q >= 0; q--) {
+                    run += hist[q];
+                    hist[q] = run;
+                }
+            }
+            group_sync<TPG>();
+            g.n_big = (int)(hist[FIT_HMAX]);
+            g.kmax = min(FIT_HMAX, xmax_all[grp]);
             if (o.method == BN_FIT_BRENT) {
                 BrentState st;
                 st.init(lower, upper);
                 bool more = true;
                 while (more) {
-                    const double val = -nb_loglik<TPG>(g, st.next, scratch, tid);
+                    const double val = -nb_loglik<TPG>(g, st.next, tab, scratch, tid);
                     nfe++;
                     more = st.step(val, o);
                 }
@@ -416,20 +477,36 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG)
                 bool more = true;
                 while (more) {
                     double val;
-                    if (st.next_is_grad) val = -nb_loglik_grad<TPG>(g, st.next, scratch, tid);
-                    else val = -nb_loglik<TPG>(g, st.next, scratch, tid);
+                    if (GRAD && st.next_is_grad) val = -nb_loglik_grad<TPG>(g, st.next, scratch, tid);
+                    else val = -nb_loglik<TPG>(g, st.next, tab, scratch, tid);
                     nfe++;
                     more = st.step(val, o);
                 }
                 res = st.next;
                 conv = st.conv;
             }
+            group_sync<TPG>(); // hist is reused by the next gene
         }
         if (tid == 0) {
             size_out[gi] = res;
             if (conv_out) conv_out[gi] = conv;
             if (nfe_out) nfe_out[gi] = nfe;
         }
+    }
+}
+
+// largest beta (decides between the series and the table form of log1p per evaluation)
+__global__ void __launch_bounds__(1024) k_max_vec(int64_t n, const double *__restrict__ v, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double m = 0.0;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) m = fmax(m, v[k]);
+    m = bn_warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; k++) m = fmax(m, sh[k]);
+        out[0] = m;
     }
 }
 
@@ -482,17 +559,26 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     DevBuf<unsigned long long> q;
     BN_TRY(q.alloc(ctx, 1));
     BN_CUDA(ctx, cudaMemsetAsync(q.p, 0, 8, ctx->stream));
+    DevBuf<double> bmax;
+    BN_TRY(bmax.alloc(ctx, 1));
+    BN_LAUNCH(ctx, k_max_vec, 1, 1024, 0, m->C, d_beta, bmax.p);
+    double beta_max = 1.0;
+    BN_CUDA(ctx, cudaMemcpyAsync(&beta_max, bmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BN_TRY(bn_sync(ctx));
     const int sms = ctx->prop.multiProcessorCount;
+    const bool grad = o.use_gradient != 0;
+#define FIT_ARGS m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0, lower, upper, beta_max, o, q.p, d_size_out, d_conv, d_nfe
     if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
-        const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 8);
-        BN_LAUNCH(ctx, k_fit_size<256>, grid, 256, 0, m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0,
-                  lower, upper, o, q.p, d_size_out, d_conv, d_nfe);
+        const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);
+        if (grad) BN_LAUNCH(ctx, (k_fit_size<256, true>), grid, 256, 0, FIT_ARGS);
+        else BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
     } else {
-        const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 16);
-        BN_LAUNCH(ctx, k_fit_size<32>, grid, 128, 0, m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0,
-                  lower, upper, o, q.p, d_size_out, d_conv, d_nfe);
+        const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 24);
+        if (grad) BN_LAUNCH(ctx, (k_fit_size<32, true>), grid, 128, 0, FIT_ARGS);
+        else BN_LAUNCH(ctx, (k_fit_size<32, false>), grid, 128, 0, FIT_ARGS);
     }
+#undef FIT_ARGS
     return BN_OK;
 }
 
@@ -594,4 +680,32 @@ extern "C" int bn_gradient_nb_2d(bn_ctx *ctx, const double SIZE_MU[2], const dou
     BN_TRY(dense_gene(ctx, 1, SIZE_MU[0], SIZE_MU[1], m_observed, BETA, n, out));
     // out may be host or device; element 1 written by a second launch
     return dense_gene(ctx, 2, SIZE_MU[0], SIZE_MU[1], m_observed, BETA, n, out + 1);
+}
+
+// ---------------------------------------------------------------------------------
+// debug hook: the device logarithms on a vector, so tests can pin them against mpmath.
+// which: 0 = bn_log, 1 = bn_log1p_pos, 2 = bn_log1p_small, 3 = bn_lgamma_stirling
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_debug_log(int which, int64_t n, const double *__restrict__ x, double *__restrict__ out)
+{
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    bn_log_table_load(tab);
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += gridDim.x * (int64_t)blockDim.x) {
+        const double v = x[k];
+        out[k] = which == 0 ? bn_log(v, tab) : which == 1 ? bn_log1p_pos(v, tab) : which == 2 ? bn_log1p_small(v) : bn_lgamma_stirling(v, tab);
+    }
+}
+
+extern "C" int bn_debug_log(bn_ctx *ctx, int which, const double *x, int64_t n, double *out)
+{
+    if (!ctx || !x || !out || n <= 0 || which < 0 || which > 3) return BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> dx;
+    BN_TRY(dx.bind(ctx, x, (size_t)n));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, out, (size_t)n));
+    BN_LAUNCH(ctx, k_debug_log, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, which, n, dx.p, o.p);
+    BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
 }

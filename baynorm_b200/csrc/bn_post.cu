@@ -24,6 +24,8 @@
 #define POST_THREADS 256
 #define POST_EPT 8
 #define POST_TG (POST_THREADS * POST_EPT)
+#define POST_NCMAX 64 // columns walked by one CTA
+#define POST_PF 4     // non-zeros per thread prefetched one column ahead (covers 1024 per tile column)
 
 enum { POST_MEAN = 0, POST_MODE = 1, POST_SAMPLE = 2 };
 
@@ -31,6 +33,32 @@ __device__ __forceinline__ double post_tempmu(double x, double size, double mu, 
 {
     const double mb = __dmul_rn(mu, beta);
     return __ddiv_rn(__dmul_rn(__dadd_rn(x, size), __dsub_rn(mu, mb)), __dadd_rn(size, mb));
+}
+
+// Posterior mode, bit-exact with the reference's operation order.
+//   reference:  floor( ((x+size)*(mu-mu*beta)/(size+mu*beta)) / (size+x) * ((size+x)-1) ) + x
+// The two IEEE divisions dominate the FP64 cost of the kernel, and floor() only needs to know on
+// which side of an integer the value lies.  Fast path: the same real-number quantity with ONE
+// approximate reciprocal (rcp.approx seed + one Newton step, relative error < 2^-44 overall);
+// if an integer lies within 2^-42 * v of it, redo the reference sequence exactly.  The fast value
+// and the reference value both differ from the real number by far less than that margin, so
+// whenever the fast path is taken floor() of both is the same integer.
+__device__ __forceinline__ double post_mode(double x, double size, double mu, double beta)
+{
+    const double r = __dadd_rn(size, x);
+    if (!(r > 1.0)) return 0.0;
+    const double mb = __dmul_rn(mu, beta);
+    const double a = __dsub_rn(mu, mb), den = __dadd_rn(size, mb), rm1 = __dsub_rn(r, 1.0);
+    // in real arithmetic the (size+x) factors cancel: v = (mu - mu*beta) * (size+x-1) / (size + mu*beta)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    y = fma(y, fma(-den, y, 1.0), y);
+    const double v = (a * rm1) * y;
+    const double fl = floor(v);
+    const double frac = v - fl, tol = fabs(v) * 2.2737367544323206e-13; // 2^-42
+    if (frac > tol && frac < 1.0 - tol) return fl + x;                    // (NaN/inf/huge fall through)
+    const double tm = __ddiv_rn(__dmul_rn(r, a), den);
+    return __dadd_rn(floor(__dmul_rn(__ddiv_rn(tm, r), rm1)), x);
 }
 
 // first index in [lo, hi) with rowidx[k] >= key
@@ -44,6 +72,11 @@ __device__ __forceinline__ int64_t lower_bound_row(const int32_t *__restrict__ r
     return lo;
 }
 
+// Dynamic shared memory: three count tiles of POST_TG doubles.  In iteration jj the CTA
+//   (1) issues the loads of column jj's non-zeros (tile slice) into registers,
+//   (2) computes and stores column jj-1 from tile (jj-1)%3 and zeroes tile (jj+1)%3,
+//   (3) scatters the prefetched non-zeros into tile jj%3 (zeroed one iteration earlier),
+// then one __syncthreads().  Global-load latency of (1) is covered by the arithmetic of (2).
 template <int MODE>
 __global__ void __launch_bounds__(POST_THREADS)
     k_posterior(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
@@ -51,9 +84,20 @@ __global__ void __launch_bounds__(POST_THREADS)
                 const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
                 int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
 {
-    __shared__ double xs[2][POST_TG];
+    extern __shared__ double xs[]; // [3][POST_TG]
+    __shared__ int64_t s_lo[POST_NCMAX], s_end[POST_NCMAX];
     const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * POST_TG;
+    const int64_t tend = t0 + POST_TG;
+    const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
+    const int nc = (int)((jb + nc_per_cta < ncol ? jb + nc_per_cta : ncol) - jb);
+    // every column's slice start, all columns in parallel (one thread each)
+    if (tid < nc) {
+        const int64_t j = col0 + jb + tid;
+        const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
+        s_lo[tid] = (t0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, t0);
+        s_end[tid] = ce;
+    }
     double sz[POST_EPT], m[POST_EPT];
 #pragma unroll
     for (int e = 0; e < POST_EPT; e++) {
@@ -61,52 +105,82 @@ __global__ void __launch_bounds__(POST_THREADS)
         sz[e] = (i < G) ? __ldg(size + i) : 1.0;
         m[e] = (i < G) ? __ldg(mu + i) : 0.0;
     }
-    const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
-    const int64_t je = (jb + nc_per_cta < ncol) ? jb + nc_per_cta : ncol;
-    int buf = 0;
-    for (int64_t jj = jb; jj < je; jj++, buf ^= 1) {
-        const int64_t j = col0 + jj;
-        double *x = xs[buf];
 #pragma unroll
-        for (int e = 0; e < POST_EPT; e++) x[e * POST_THREADS + tid] = 0.0;
-        const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
-        const int64_t lo = lower_bound_row(rowidx, cs, ce, t0);
-        const int64_t hi = lower_bound_row(rowidx, lo, ce, t0 + POST_TG);
-        __syncthreads(); // zeros visible; also orders this buffer's previous readers (2 columns ago)
-        for (int64_t k = lo + tid; k < hi; k += POST_THREADS) x[__ldg(rowidx + k) - t0] = __ldcs(val + k);
-        __syncthreads();
-        const double b = __ldg(beta + j);
-        double *o = out + G * jj;
+    for (int e = 0; e < POST_EPT; e++) {
+        xs[e * POST_THREADS + tid] = 0.0;
+        xs[POST_TG + e * POST_THREADS + tid] = 0.0;
+    }
+    __syncthreads();
+    for (int jj = 0; jj <= nc; jj++) {
+        double *xcur = xs + (jj % 3) * POST_TG;           // scatter target (column jj)
+        double *xprev = xs + ((jj + 2) % 3) * POST_TG;    // compute source (column jj-1)
+        double *xnext = xs + ((jj + 1) % 3) * POST_TG;    // zeroed for column jj+1
+        // (1) prefetch column jj's slice
+        int32_t pr[POST_PF];
+        double pv[POST_PF];
+        int64_t kbase = 0, kend = 0;
+        if (jj < nc) {
+            kbase = s_lo[jj];
+            kend = s_end[jj];
 #pragma unroll
-        for (int e = 0; e < POST_EPT; e++) {
-            const int64_t i = t0 + e * POST_THREADS + tid;
-            if (i >= G) continue;
-            const double xv = x[e * POST_THREADS + tid];
-            const double tm = post_tempmu(xv, sz[e], m[e], b);
-            if (MODE == POST_MEAN) {
-                __stcs(o + i, __dadd_rn(tm, xv));
-            } else if (MODE == POST_MODE) {
-                const double r = __dadd_rn(sz[e], xv);
-                double res = 0.0;
-                if (r > 1.0) res = __dadd_rn(floor(__dmul_rn(__ddiv_rn(tm, r), __dsub_rn(r, 1.0))), xv);
-                __stcs(o + i, res);
-            } else {
-                const double r = __dadd_rn(sz[e], xv);
-                const NBParams P = bn_nb_setup(r, tm);
-                Philox g;
-                g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
-                // one Philox counter block per 4 draws; sub-stream index = s / 4 so that the value
-                // of draw s does not depend on S
-                for (int s = 0; s < S; s++) {
-                    if ((s & 3) == 0) {
-                        g.c2 = (uint32_t)(s >> 2);
-                        g.c3 = 0;
-                        g.have = 0;
+            for (int q = 0; q < POST_PF; q++) {
+                const int64_t k = kbase + q * POST_THREADS + tid;
+                pr[q] = (k < kend) ? __ldg(rowidx + k) : 0x7fffffff;
+                pv[q] = (k < kend) ? __ldcs(val + k) : 0.0;
+            }
+        }
+        // (2) column jj-1
+        if (jj > 0) {
+            const int64_t jl = jb + jj - 1, j = col0 + jl;
+            const double b = __ldg(beta + j);
+            double *o = out + G * jl;
+#pragma unroll
+            for (int e = 0; e < POST_EPT; e++) {
+                const int64_t i = t0 + e * POST_THREADS + tid;
+                const double xv = xprev[e * POST_THREADS + tid];
+                if (i >= G) continue;
+                if (MODE == POST_MEAN) {
+                    __stcs(o + i, __dadd_rn(post_tempmu(xv, sz[e], m[e], b), xv));
+                } else if (MODE == POST_MODE) {
+                    __stcs(o + i, post_mode(xv, sz[e], m[e], b));
+                } else {
+                    const double tm = post_tempmu(xv, sz[e], m[e], b);
+                    const double r = __dadd_rn(sz[e], xv);
+                    const NBParams P = bn_nb_setup(r, tm);
+                    Philox g;
+                    g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
+                    // one Philox counter block per 4 draws; sub-stream index = s / 4 so that the value
+                    // of draw s does not depend on S
+                    for (int s = 0; s < S; s++) {
+                        if ((s & 3) == 0) {
+                            g.c2 = (uint32_t)(s >> 2);
+                            g.c3 = 0;
+                            g.have = 0;
+                        }
+                        __stcs(o + i + sstride * s, bn_nb_draw(P, g) + xv);
                     }
-                    __stcs(o + i + sstride * s, bn_nb_draw(P, g) + xv);
                 }
             }
         }
+#pragma unroll
+        for (int e = 0; e < POST_EPT; e++) xnext[e * POST_THREADS + tid] = 0.0;
+        // (3) scatter column jj
+        if (jj < nc) {
+            bool more = true;
+#pragma unroll
+            for (int q = 0; q < POST_PF; q++) {
+                if ((int64_t)pr[q] < tend) xcur[pr[q] - t0] = pv[q];
+                else more = false;
+            }
+            if (more) { // dense tile column: the rest of the slice
+                for (int64_t k = kbase + POST_PF * POST_THREADS + tid; k < kend; k += POST_THREADS) {
+                    const int64_t r = __ldg(rowidx + k);
+                    if (r >= tend) break;
+                    xcur[r - t0] = __ldcs(val + k);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -126,22 +200,28 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     DevOut<double> o;
     BN_TRY(o.bind(ctx, out, nout));
     const int64_t tiles = (m->G + POST_TG - 1) / POST_TG;
-    // enough CTAs to fill 148 SMs a few times over, but long enough column walks to amortise
-    // the size/mu register loads
-    int nc = 16;
+    // long column walks amortise the per-CTA slice search and the size/mu loads; keep >= ~8 CTAs per SM
+    int nc = POST_NCMAX;
     while (nc > 1 && tiles * ((ncol + nc - 1) / nc) < 148 * 8) nc >>= 1;
-    const int64_t gy = (ncol + nc - 1) / nc;
-    if (gy > 65535) nc = (int)((ncol + 65534) / 65535);
+    if ((ncol + nc - 1) / nc > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
     dim3 grid((unsigned)tiles, (unsigned)((ncol + nc - 1) / nc));
     const int64_t sstride = m->G * ncol;
+    const size_t smem = 3 * POST_TG * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
     if (mode == POST_MEAN)
-        BN_LAUNCH(ctx, k_posterior<POST_MEAN>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+        BN_LAUNCH(ctx, k_posterior<POST_MEAN>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
                   col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
     else if (mode == POST_MODE)
-        BN_LAUNCH(ctx, k_posterior<POST_MODE>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+        BN_LAUNCH(ctx, k_posterior<POST_MODE>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
                   col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
     else
-        BN_LAUNCH(ctx, k_posterior<POST_SAMPLE>, grid, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
+        BN_LAUNCH(ctx, k_posterior<POST_SAMPLE>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
                   col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
     BN_TRY(o.commit(ctx));
     return bn_sync(ctx);

@@ -220,6 +220,9 @@ BN_API int bn_debug_fp64_peak(bn_ctx *ctx, double *flops_per_s);
 /* ---- debug ------------------------------------------------------------------------- */
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
  * generator against the published known-answer vectors. */
+/* The device logarithms of the likelihood kernels on a vector (which: 0 log, 1 log1p for y >= 0,
+ * 2 log1p series for y <= 2^-6, 3 Stirling lgamma for z >= 64). */
+BN_API int bn_debug_log(bn_ctx *ctx, int which, const double *x, int64_t n, double *out);
 BN_API int bn_debug_philox(bn_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 #ifdef __cplusplus

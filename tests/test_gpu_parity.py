@@ -46,6 +46,42 @@ def test_philox_known_answers(bn, ctx):
         assert tuple(int(v) for v in o) == want
 
 
+def test_device_log(bn, ctx):
+    """The table-driven FP64 logarithms of the fit kernel against 50-digit mpmath."""
+    import ctypes as C
+    import mpmath as mp
+    mp.mp.dps = 50
+    rng = np.random.default_rng(0)
+
+    def run(which, x):
+        x = np.ascontiguousarray(x, np.float64)
+        o = np.zeros_like(x)
+        ctx.check(ctx.lib.bn_debug_log(ctx.h, which, C.c_void_p(x.ctypes.data), x.size, C.c_void_p(o.ctypes.data)))
+        return o
+
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-300), np.log(1e300), 4000)), rng.uniform(0.5, 2.0, 4000),
+                        1 + rng.uniform(-1, 1, 2000) * 1e-6, [1.0, 0.6875, 1.375, 2.0, 0.5, 1e-3, 64.0]])
+    got = run(0, x)
+    ex = np.array([float(mp.log(mp.mpf(float(v)))) for v in x])
+    err = np.abs(got - ex)
+    assert (err <= 2.5e-16 * np.abs(ex) + 2e-18).all(), float((err / (2.5e-16 * np.abs(ex) + 2e-18)).max())
+    mod = (x > 1e-6) & (x < 1e6)          # the range the likelihood uses: within 1 ulp
+    assert (err[mod] <= 2.3e-16 * np.abs(ex[mod]) + 2e-18).all()     # <= 1 ulp (an ulp is 1.1e-16 .. 2.2e-16 relative)
+    y = np.concatenate([np.exp(rng.uniform(np.log(1e-30), np.log(1e6), 6000)), rng.uniform(0, 3, 3000), [0.0, 1.0, 1e-17]])
+    got = run(1, y)
+    ex = np.array([float(mp.log1p(mp.mpf(float(v)))) for v in y])
+    err = np.abs(got - ex)
+    assert (err <= 2.3e-16 * np.abs(ex) + 2e-18).all(), float((err / (2.3e-16 * np.abs(ex) + 2e-18)).max())
+    ys = np.concatenate([np.exp(rng.uniform(np.log(1e-30), np.log(2.0 ** -6), 4000)), [0.0, 2.0 ** -6]])
+    got = run(2, ys)
+    ex = np.array([float(mp.log1p(mp.mpf(float(v)))) for v in ys])
+    assert (np.abs(got - ex) <= 2.3e-16 * np.abs(ex)).all()
+    z = np.concatenate([rng.uniform(64, 200, 2000), np.exp(rng.uniform(np.log(64), np.log(1e7), 2000))])
+    got = run(3, z)
+    ex = np.array([float(mp.loggamma(mp.mpf(float(v)))) for v in z])
+    assert (np.abs(got - ex) <= 3e-16 * np.abs(ex)).all()
+
+
 def test_upload_roundtrip_and_validation(bn, ctx, small, oracle):
     Mo = small["Mo"]
     for p in (Mo.p.astype(np.int32), Mo.p):
