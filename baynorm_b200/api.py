@@ -162,7 +162,8 @@ class DeviceMatrix:
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.bn_mat_free(self.h)
+            if getattr(self.ctx, "h", None):      # frees are ordered on the context's stream
+                self.ctx.lib.bn_mat_free(self.h)
             self.h = None
 
     def __del__(self):

@@ -209,9 +209,9 @@ extern "C" int bn_mat_from_csc(bn_ctx *ctx, int64_t G, int64_t C, const void *p,
         return rc;
     };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&m->colptr, (size_t)(C + 1) * 8)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&m->colptr, (size_t)(C + 1) * 8, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "matrix allocation failed: %s", cudaGetErrorString(e)));
     if (p_is_int64) {
         if ((e = cudaMemcpyAsync(m->colptr, p, (size_t)(C + 1) * 8, cudaMemcpyDefault, ctx->stream)) != cudaSuccess)
@@ -290,7 +290,7 @@ extern "C" int bn_mat_from_dense(bn_ctx *ctx, int64_t G, int64_t C, const double
         return rc;
     };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&m->colptr, (size_t)(C + 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&m->colptr, (size_t)(C + 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "colptr: %s", cudaGetErrorString(e)));
     DevBuf<int64_t> cnt;
     int rc = cnt.alloc(ctx, (size_t)C + 1);
@@ -311,8 +311,8 @@ extern "C" int bn_mat_from_dense(bn_ctx *ctx, int64_t G, int64_t C, const double
         return fail(bn_fail(ctx, BN_ERR_CUDA, "dense scan: %s", cudaGetErrorString(e)));
     if (nnz >= 4294967295LL) return fail(bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard"));
     m->nnz = nnz;
-    if ((e = cudaMalloc((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "matrix allocation failed: %s", cudaGetErrorString(e)));
     k_dense_fill<<<blocks, 256, 0, ctx->stream>>>(G, C, A.p, m->colptr, m->rowidx, m->val);
     ctx->launches++;
@@ -324,16 +324,19 @@ extern "C" int bn_mat_from_dense(bn_ctx *ctx, int64_t G, int64_t C, const double
 extern "C" void bn_mat_free(bn_mat *m)
 {
     if (!m) return;
+    // stream-ordered frees: the memory returns to the context's pool once the work already queued
+    // on the stream has finished, and the next matrix re-uses it without going to the driver
     if (m->ctx) {
         cudaSetDevice(m->ctx->device);
-        cudaStreamSynchronize(m->ctx->stream);
+        cudaStream_t st = m->ctx->stream;
+        if (m->colptr) cudaFreeAsync(m->colptr, st);
+        if (m->rowidx) cudaFreeAsync(m->rowidx, st);
+        if (m->val) cudaFreeAsync(m->val, st);
+        if (m->rowptr) cudaFreeAsync(m->rowptr, st);
+        if (m->gm) cudaFreeAsync(m->gm, st);
+        if (m->cell) cudaFreeAsync(m->cell, st);
+        if (m->rval) cudaFreeAsync(m->rval, st);
     }
-    cudaFree(m->colptr);
-    cudaFree(m->rowidx);
-    cudaFree(m->val);
-    cudaFree(m->rowptr);
-    cudaFree(m->cell);
-    cudaFree(m->rval);
     delete m;
 }
 
@@ -354,10 +357,12 @@ extern "C" int bn_mat_drop_gene_major(bn_mat *m)
     if (!m) return BN_ERR_INVALID;
     if (m->has_csr) {
         cudaSetDevice(m->ctx->device);
-        cudaStreamSynchronize(m->ctx->stream);
-        cudaFree(m->rowptr);
-        cudaFree(m->cell);
-        cudaFree(m->rval);
+        cudaStream_t st = m->ctx->stream;
+        if (m->rowptr) cudaFreeAsync(m->rowptr, st);
+        if (m->gm) cudaFreeAsync(m->gm, st);
+        if (m->cell) cudaFreeAsync(m->cell, st);
+        if (m->rval) cudaFreeAsync(m->rval, st);
+        m->gm = nullptr;
         m->rowptr = nullptr;
         m->cell = nullptr;
         m->rval = nullptr;
@@ -474,7 +479,7 @@ extern "C" int bn_mat_select_cols(bn_ctx *ctx, const bn_mat *m, const int64_t *i
         return rc;
     };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&s->colptr, (size_t)(n + 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&s->colptr, (size_t)(n + 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "colptr: %s", cudaGetErrorString(e)));
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, s->colptr, (int)(n + 1), ctx->stream);
@@ -491,8 +496,8 @@ extern "C" int bn_mat_select_cols(bn_ctx *ctx, const bn_mat *m, const int64_t *i
         return fail(bn_fail(ctx, BN_ERR_CUDA, "select_cols: %s", cudaGetErrorString(e)));
     if (hbad) return fail(bn_fail(ctx, BN_ERR_INVALID, "column index out of range"));
     s->nnz = nnz;
-    if ((e = cudaMalloc((void **)&s->rowidx, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&s->val, (size_t)(nnz ? nnz : 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&s->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void **)&s->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "matrix allocation failed: %s", cudaGetErrorString(e)));
     const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 16);
     k_sel_copy<<<blocks, 256, 0, ctx->stream>>>(m->colptr, m->rowidx, m->val, di.p, n, s->colptr, s->rowidx, s->val);
@@ -536,14 +541,27 @@ __global__ void k_csr_gather(int64_t nnz, int64_t C, const uint32_t *__restrict_
     }
 }
 
+// (cell << 32) | count for every non-zero, in CSC order: one warp per column
+__global__ void __launch_bounds__(256) k_pack_nz(int64_t C, const int64_t *__restrict__ colptr, const double *__restrict__ val,
+                                                 uint64_t *__restrict__ packed)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    for (int64_t j = warp; j < C; j += nwarp) {
+        const int64_t a = colptr[j], b = colptr[j + 1];
+        const uint64_t hi = (uint64_t)j << 32;
+        for (int64_t k = a + lane; k < b; k += 32) packed[k] = hi | (uint64_t)(uint32_t)__ldcs(val + k);
+    }
+}
+
 int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
 {
     if (m->has_csr) return BN_OK;
     cudaSetDevice(ctx->device);
     const int64_t nnz = m->nnz, G = m->G;
-    BN_CUDA(ctx, cudaMalloc((void **)&m->rowptr, (size_t)(G + 1) * 8));
-    BN_CUDA(ctx, cudaMalloc((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4));
-    BN_CUDA(ctx, cudaMalloc((void **)&m->rval, (size_t)(nnz ? nnz : 1) * 8));
+    if (nnz > 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz > 2^31-1 per shard in the gene-major build");
+    BN_CUDA(ctx, cudaMallocAsync((void **)&m->rowptr, (size_t)(G + 1) * 8, ctx->stream));
     // row pointer = exclusive scan of the row histogram
     DevBuf<unsigned long long> cnt;
     BN_TRY(cnt.alloc(ctx, (size_t)G + 1));
@@ -557,27 +575,47 @@ int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
         cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const int64_t *)cnt.p, m->rowptr, (int)(G + 1), ctx->stream);
         ctx->launches++;
     }
-    if (nnz) {
-        DevBuf<int32_t> k0, k1;
-        DevBuf<uint32_t> v0, v1;
-        BN_TRY(k0.alloc(ctx, (size_t)nnz));
-        BN_TRY(k1.alloc(ctx, (size_t)nnz));
-        BN_TRY(v0.alloc(ctx, (size_t)nnz));
-        BN_TRY(v1.alloc(ctx, (size_t)nnz));
-        BN_CUDA(ctx, cudaMemcpyAsync(k0.p, m->rowidx, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        BN_LAUNCH(ctx, k_iota_u32, (unsigned)((nnz + 255) / 256), 256, 0, v0.p, nnz);
-        int bits = 1;
-        while ((1LL << bits) < G) bits++;
-        cub::DoubleBuffer<int32_t> dk(k0.p, k1.p);
-        cub::DoubleBuffer<uint32_t> dv(v0.p, v1.p);
-        size_t tb = 0;
-        if (nnz > 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz > 2^31-1 per shard in the gene-major build");
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)nnz, 0, bits, ctx->stream);
-        DevBuf<char> tmp;
-        BN_TRY(tmp.alloc(ctx, tb));
-        BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)nnz, 0, bits, ctx->stream));
-        ctx->launches += (bits + 7) / 8 + 1;
-        BN_LAUNCH(ctx, k_csr_gather, 148 * 8, 256, 0, nnz, m->C, dv.Current(), m->colptr, m->val, m->cell, m->rval);
+    int bits = 1;
+    while ((1LL << bits) < G) bits++;
+    if (m->is_count) {
+        // stable sort of (row -> packed (cell, count)) pairs: the sorted values ARE the gene-major matrix
+        BN_CUDA(ctx, cudaMallocAsync((void **)&m->gm, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
+        if (nnz) {
+            DevBuf<uint64_t> packed;
+            DevBuf<int32_t> kout;
+            BN_TRY(packed.alloc(ctx, (size_t)nnz));
+            BN_TRY(kout.alloc(ctx, (size_t)nnz));
+            const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
+            BN_LAUNCH(ctx, k_pack_nz, blocks, 256, 0, m->C, m->colptr, m->val, packed.p);
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, (const int32_t *)m->rowidx, kout.p, (const uint64_t *)packed.p, m->gm,
+                                            (int)nnz, 0, bits, ctx->stream);
+            DevBuf<char> tmp;
+            BN_TRY(tmp.alloc(ctx, tb));
+            BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p,
+                                                         (const uint64_t *)packed.p, m->gm, (int)nnz, 0, bits, ctx->stream));
+            ctx->launches += (bits + 7) / 8 + 1;
+        }
+    } else {
+        BN_CUDA(ctx, cudaMallocAsync((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
+        BN_CUDA(ctx, cudaMallocAsync((void **)&m->rval, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
+        if (nnz) {
+            DevBuf<int32_t> kout;
+            DevBuf<uint32_t> v0, v1;
+            BN_TRY(kout.alloc(ctx, (size_t)nnz));
+            BN_TRY(v0.alloc(ctx, (size_t)nnz));
+            BN_TRY(v1.alloc(ctx, (size_t)nnz));
+            BN_LAUNCH(ctx, k_iota_u32, (unsigned)((nnz + 255) / 256), 256, 0, v0.p, nnz);
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, (const int32_t *)m->rowidx, kout.p, (const uint32_t *)v0.p, v1.p,
+                                            (int)nnz, 0, bits, ctx->stream);
+            DevBuf<char> tmp;
+            BN_TRY(tmp.alloc(ctx, tb));
+            BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p, (const uint32_t *)v0.p,
+                                                         v1.p, (int)nnz, 0, bits, ctx->stream));
+            ctx->launches += (bits + 7) / 8 + 1;
+            BN_LAUNCH(ctx, k_csr_gather, 148 * 8, 256, 0, nnz, m->C, v1.p, m->colptr, m->val, m->cell, m->rval);
+        }
     }
     m->has_csr = true;
     return BN_OK;

@@ -22,19 +22,22 @@
 #include "bn_internal.cuh"
 #include "bn_math.cuh"
 
-#define FIT_HMAX 64 // counts up to here go through the tail table, larger ones through Stirling
+// counts up to HMAX go through the tail table (one logarithm per table entry per evaluation, shared
+// by all non-zeros of the gene), larger ones through Stirling's series
+template <int TPG> struct FitCfg {
+    static constexpr int HMAX = (TPG == 32) ? 64 : 256;
+};
 
 struct FitGene {
-    const int32_t *cell; // this gene's non-zeros
-    const double *rval;
+    const uint64_t *nz; // this gene's non-zeros, (cell << 32) | count
     int64_t nnz;
     const double *beta, *logbeta;
     int64_t C;
     double mu, lmu;
     double Kc;             // sum x*log(mu*beta_j) - sum lgamma(x+1): does not depend on phi
     double beta_max;
-    const uint32_t *tail;  // shared memory: tail[k] = #{non-zeros with x > k}, k < FIT_HMAX
-    int kmax;              // min(FIT_HMAX, largest count)
+    const uint32_t *tail;  // shared memory: tail[k] = #{non-zeros with x > k}, k < HMAX
+    int kmax;              // min(HMAX, largest count)
     int n_big;             // non-zeros with x > FIT_HMAX
 };
 
@@ -47,40 +50,66 @@ template <int TPG>
 __device__ double nb_loglik(const FitGene &g, double phi, const BnLogEntry *__restrict__ tab, double *scratch, int tid)
 {
     const double r = g.mu / phi;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // Dense part: sum_j log(1 + r beta_j) = log prod_j (1 + r beta_j).  Four independent running
+    // products per thread, folded through ONE logarithm every FOLD factors: 2 FP64 instructions per
+    // cell (fma, mul) instead of a 15-instruction log1p.  Each multiplication perturbs the logarithm
+    // of the product by <= 2^-53 absolute, the same size as one rounding of the sum it replaces and
+    // far below one ulp of l(phi); FOLD keeps the product inside the double range:
+    // (1 + r beta_max)^16 < 2^1008 whenever r beta_max < 2^63.
+    const double umax = fma(r, g.beta_max, 1.0);
+    const int fold = umax < 9.0e18 ? 16 : (umax < 1.0e75 ? 4 : 1);
+    double a0 = 0.0, a1 = 0.0;
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
     int64_t j = tid;
-    if (r * g.beta_max <= 0.015625) {
-        for (; j + 3 * TPG < g.C; j += 4 * TPG) {
-            a0 += bn_log1p_small(r * __ldg(g.beta + j));
-            a1 += bn_log1p_small(r * __ldg(g.beta + j + TPG));
-            a2 += bn_log1p_small(r * __ldg(g.beta + j + 2 * TPG));
-            a3 += bn_log1p_small(r * __ldg(g.beta + j + 3 * TPG));
+    int cnt = 0;
+    for (; j + 3 * TPG < g.C; j += 4 * TPG) {
+        p0 *= fma(r, __ldg(g.beta + j), 1.0);
+        p1 *= fma(r, __ldg(g.beta + j + TPG), 1.0);
+        p2 *= fma(r, __ldg(g.beta + j + 2 * TPG), 1.0);
+        p3 *= fma(r, __ldg(g.beta + j + 3 * TPG), 1.0);
+        if (++cnt == fold) {
+            a0 += bn_log(p0, tab) + bn_log(p1, tab);
+            a1 += bn_log(p2, tab) + bn_log(p3, tab);
+            p0 = p1 = p2 = p3 = 1.0;
+            cnt = 0;
         }
-        for (; j < g.C; j += TPG) a0 += bn_log1p_small(r * __ldg(g.beta + j));
-    } else {
-        for (; j + 3 * TPG < g.C; j += 4 * TPG) {
-            a0 += bn_log1p_pos(r * __ldg(g.beta + j), tab);
-            a1 += bn_log1p_pos(r * __ldg(g.beta + j + TPG), tab);
-            a2 += bn_log1p_pos(r * __ldg(g.beta + j + 2 * TPG), tab);
-            a3 += bn_log1p_pos(r * __ldg(g.beta + j + 3 * TPG), tab);
-        }
-        for (; j < g.C; j += TPG) a0 += bn_log1p_pos(r * __ldg(g.beta + j), tab);
     }
+    for (; j < g.C; j += TPG) {
+        p0 *= fma(r, __ldg(g.beta + j), 1.0);
+        if (++cnt >= fold) {
+            a0 += bn_log(p0, tab);
+            p0 = 1.0;
+            cnt = 0;
+        }
+    }
+    a0 += bn_log(p0, tab) + bn_log(p1, tab);
+    a1 += bn_log(p2, tab) + bn_log(p3, tab);
+    const double a2 = 0.0, a3 = 0.0;
     double acc = -phi * ((a0 + a1) + (a2 + a3));
+    constexpr int HMAX = FitCfg<TPG>::HMAX;
     double s0 = 0.0, s1 = 0.0;
     int64_t k = tid;
-    if (g.n_big == 0) {
-        for (; k + TPG < g.nnz; k += 2 * TPG) {
-            s0 = fma(-g.rval[k], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
-            s1 = fma(-g.rval[k + TPG], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k + TPG]), phi), tab), s1);
-        }
-        for (; k < g.nnz; k += TPG) s0 = fma(-g.rval[k], bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
-    } else {
-        const double lgref = bn_lgamma_stirling(phi + (double)FIT_HMAX, tab);
-        for (; k < g.nnz; k += TPG) {
-            const double x = g.rval[k];
-            s0 = fma(-x, bn_log(fma(g.mu, __ldg(g.beta + g.cell[k]), phi), tab), s0);
-            if (x > (double)FIT_HMAX) s1 += bn_lgamma_stirling(x + phi, tab) - lgref;
+    // non-zeros: x_j log(phi + mu beta_j); the packed words and the beta gathers of four non-zeros
+    // are in flight together (the gather address depends on the packed word)
+    for (; k + 3 * TPG < g.nnz; k += 4 * TPG) {
+        const uint64_t e0 = __ldg(g.nz + k), e1 = __ldg(g.nz + k + TPG), e2 = __ldg(g.nz + k + 2 * TPG),
+                       e3 = __ldg(g.nz + k + 3 * TPG);
+        const double b0 = __ldg(g.beta + (e0 >> 32)), b1 = __ldg(g.beta + (e1 >> 32)), b2 = __ldg(g.beta + (e2 >> 32)),
+                     b3 = __ldg(g.beta + (e3 >> 32));
+        s0 = fma(-(double)(uint32_t)e0, bn_log(fma(g.mu, b0, phi), tab), s0);
+        s1 = fma(-(double)(uint32_t)e1, bn_log(fma(g.mu, b1, phi), tab), s1);
+        s0 = fma(-(double)(uint32_t)e2, bn_log(fma(g.mu, b2, phi), tab), s0);
+        s1 = fma(-(double)(uint32_t)e3, bn_log(fma(g.mu, b3, phi), tab), s1);
+    }
+    for (; k < g.nnz; k += TPG) {
+        const uint64_t e0 = __ldg(g.nz + k);
+        s0 = fma(-(double)(uint32_t)e0, bn_log(fma(g.mu, __ldg(g.beta + (e0 >> 32)), phi), tab), s0);
+    }
+    if (g.n_big != 0) { // rare: counts above the tail table, lgamma(x+phi) - lgamma(HMAX+phi) by Stirling
+        const double lgref = bn_lgamma_stirling(phi + (double)HMAX, tab);
+        for (k = tid; k < g.nnz; k += TPG) {
+            const double x = (double)(uint32_t)__ldg(g.nz + k);
+            if (x > (double)HMAX) s1 += bn_lgamma_stirling(x + phi, tab) - lgref;
         }
     }
     for (int q = tid; q < g.kmax; q += TPG) s1 = fma((double)g.tail[q], bn_log(phi + (double)q, tab), s1);
@@ -112,8 +141,9 @@ template <int TPG> __device__ double nb_loglik_grad(const FitGene &g, double phi
     const double dgphi = bn_digamma(phi);
     double sp = 0.0;
     for (int64_t k = tid; k < g.nnz; k += TPG) {
-        const double x = g.rval[k];
-        const double m = g.mu * __ldg(g.beta + g.cell[k]);
+        const uint64_t e0 = __ldg(g.nz + k);
+        const double x = (double)(uint32_t)e0;
+        const double m = g.mu * __ldg(g.beta + (e0 >> 32));
         double dd;
         if (x <= 16.0) {
             dd = 0.0;
@@ -384,18 +414,19 @@ template <int TPG> __device__ __forceinline__ void group_sync()
 }
 
 template <int TPG, bool GRAD>
-__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
-    k_fit_size(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ cell,
-               const double *__restrict__ rval, const double *__restrict__ beta, const double *__restrict__ logbeta,
+__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
+    k_fit_size(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
+               const double *__restrict__ beta, const double *__restrict__ logbeta,
                const double *__restrict__ mu0, const double *__restrict__ size0, double lower, double upper,
                double beta_max, FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
                int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
 {
     constexpr int NGROUP = (TPG == 32) ? 4 : 1;
+    constexpr int HMAX = FitCfg<TPG>::HMAX;
     __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
     __shared__ double scratch[8];
     __shared__ unsigned long long next_gene;
-    __shared__ uint32_t hist_all[NGROUP][FIT_HMAX + 1];
+    __shared__ uint32_t hist_all[NGROUP][HMAX + 1];
     __shared__ int xmax_all[NGROUP];
     bn_log_table_load(tab);
     __syncthreads();
@@ -417,8 +448,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
         const int64_t gi = (int64_t)gq;
         FitGene g;
         const int64_t a = rowptr[gi];
-        g.cell = cell + a;
-        g.rval = rval + a;
+        g.nz = gm + a;
         g.nnz = rowptr[gi + 1] - a;
         g.beta = beta;
         g.logbeta = logbeta;
@@ -435,15 +465,16 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
             if (o.method == BN_FIT_SPG) nfe = 2;
         } else {
             // per-gene constants: count histogram -> tail table, Kc, largest count
-            for (int q = tid; q <= FIT_HMAX; q += TPG) hist[q] = 0;
+            for (int q = tid; q <= HMAX; q += TPG) hist[q] = 0;
             if (tid == 0) xmax_all[grp] = 0;
             group_sync<TPG>();
             double kk = 0.0;
             int xm = 0;
             for (int64_t k = tid; k < g.nnz; k += TPG) {
-                const double x = g.rval[k];
-                kk += x * (g.lmu + __ldg(logbeta + g.cell[k])) - lgamma(x + 1.0);
-                const int xi = x > (double)FIT_HMAX ? FIT_HMAX + 1 : (int)x;
+                const uint64_t e0 = __ldg(g.nz + k);
+                const double x = (double)(uint32_t)e0;
+                kk += x * (g.lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
+                const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
                 atomicAdd(&hist[xi - 1], 1u);
                 xm = max(xm, xi);
             }
@@ -451,15 +482,15 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
             g.Kc = bn_group_sum<TPG>(kk, scratch);
             group_sync<TPG>();
             if (tid == 0) { // suffix sum: tail[k] = #{x > k}
-                uint32_t run = hist[FIT_HMAX];
-                for (int q = FIT_HMAX - 1; q >= 0; q--) {
+                uint32_t run = hist[HMAX];
+                for (int q = HMAX - 1; q >= 0; q--) {
                     run += hist[q];
                     hist[q] = run;
                 }
             }
             group_sync<TPG>();
-            g.n_big = (int)(hist[FIT_HMAX]);
-            g.kmax = min(FIT_HMAX, xmax_all[grp]);
+            g.n_big = (int)(hist[HMAX]);
+            g.kmax = min(HMAX, xmax_all[grp]);
             if (o.method == BN_FIT_BRENT) {
                 BrentState st;
                 st.init(lower, upper);
@@ -567,7 +598,7 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     BN_TRY(bn_sync(ctx));
     const int sms = ctx->prop.multiProcessorCount;
     const bool grad = o.use_gradient != 0;
-#define FIT_ARGS m->G, m->C, m->rowptr, m->cell, m->rval, d_beta, lb.p, d_mu0, d_size0, lower, upper, beta_max, o, q.p, d_size_out, d_conv, d_nfe
+#define FIT_ARGS m->G, m->C, m->rowptr, m->gm, d_beta, lb.p, d_mu0, d_size0, lower, upper, beta_max, o, q.p, d_size_out, d_conv, d_nfe
     if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
         const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);

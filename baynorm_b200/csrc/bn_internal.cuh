@@ -36,7 +36,11 @@ struct bn_mat {
     // gene-major twin (built on demand by bn_mat_ensure_csr)
     bool has_csr = false;
     int64_t *rowptr = nullptr; // [G+1]
-    int32_t *cell = nullptr;   // [nnz] cell index, increasing within a gene
+    // count matrices (is_count): one packed word per non-zero, (cell << 32) | count, cells
+    // increasing within a gene -- 8 B per non-zero for every per-gene stage
+    uint64_t *gm = nullptr;    // [nnz]
+    // general real-valued matrices (EstPrior on already normalised data): separate arrays
+    int32_t *cell = nullptr;   // [nnz]
     double *rval = nullptr;    // [nnz]
 };
 

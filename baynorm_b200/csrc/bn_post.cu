@@ -17,13 +17,12 @@
 //   mode   = floor((tempmu / (size + x)) * ((size + x) - 1)) + x       (:1281), 0 if size+x <= 1
 #include <cub/cub.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include "bn_internal.cuh"
 #include "bn_rng.cuh"
 
 #define POST_THREADS 256
-#define POST_EPT 8
-#define POST_TG (POST_THREADS * POST_EPT)
 #define POST_NCMAX 64 // columns walked by one CTA
 #define POST_PF 4     // non-zeros per thread prefetched one column ahead (covers 1024 per tile column)
 
@@ -77,13 +76,14 @@ __device__ __forceinline__ int64_t lower_bound_row(const int32_t *__restrict__ r
 //   (2) computes and stores column jj-1 from tile (jj-1)%3 and zeroes tile (jj+1)%3,
 //   (3) scatters the prefetched non-zeros into tile jj%3 (zeroed one iteration earlier),
 // then one __syncthreads().  Global-load latency of (1) is covered by the arithmetic of (2).
-template <int MODE>
-__global__ void __launch_bounds__(POST_THREADS)
+template <int MODE, int POST_EPT>
+__global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
     k_posterior(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                 const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
                 const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
                 int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
 {
+    constexpr int POST_TG = POST_THREADS * POST_EPT;
     extern __shared__ double xs[]; // [3][POST_TG]
     __shared__ int64_t s_lo[POST_NCMAX], s_end[POST_NCMAX];
     const int tid = threadIdx.x;
@@ -199,30 +199,36 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     BN_TRY(mm.bind(ctx, mu, (size_t)m->G));
     DevOut<double> o;
     BN_TRY(o.bind(ctx, out, nout));
-    const int64_t tiles = (m->G + POST_TG - 1) / POST_TG;
+    static int ept = 0;
+    if (!ept) {
+        const char *e = getenv("BN_POST_EPT");
+        ept = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    const int64_t TG = (int64_t)POST_THREADS * ept;
+    const int64_t tiles = (m->G + TG - 1) / TG;
     // long column walks amortise the per-CTA slice search and the size/mu loads; keep >= ~8 CTAs per SM
     int nc = POST_NCMAX;
     while (nc > 1 && tiles * ((ncol + nc - 1) / nc) < 148 * 8) nc >>= 1;
     if ((ncol + nc - 1) / nc > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
     dim3 grid((unsigned)tiles, (unsigned)((ncol + nc - 1) / nc));
     const int64_t sstride = m->G * ncol;
-    const size_t smem = 3 * POST_TG * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<POST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+    const size_t smem = 3 * (size_t)TG * sizeof(double);
+#define POST_GO(MODE_, EPT_)                                                                                         \
+    do {                                                                                                             \
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<MODE_, EPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        BN_LAUNCH(ctx, (k_posterior<MODE_, EPT_>), grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, \
+                  mm.p, col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);                                  \
+    } while (0)
+    if (ept == 8) {
+        if (mode == POST_MEAN) POST_GO(POST_MEAN, 8);
+        else if (mode == POST_MODE) POST_GO(POST_MODE, 8);
+        else POST_GO(POST_SAMPLE, 8);
+    } else {
+        if (mode == POST_MEAN) POST_GO(POST_MEAN, 4);
+        else if (mode == POST_MODE) POST_GO(POST_MODE, 4);
+        else POST_GO(POST_SAMPLE, 4);
     }
-    if (mode == POST_MEAN)
-        BN_LAUNCH(ctx, k_posterior<POST_MEAN>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
-                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
-    else if (mode == POST_MODE)
-        BN_LAUNCH(ctx, k_posterior<POST_MODE>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
-                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
-    else
-        BN_LAUNCH(ctx, k_posterior<POST_SAMPLE>, grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
-                  col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);
+#undef POST_GO
     BN_TRY(o.commit(ctx));
     return bn_sync(ctx);
 }
@@ -356,7 +362,7 @@ extern "C" int bn_mat_synth_nb(bn_ctx *ctx, int64_t G, int64_t C, const double *
         return rc;
     };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&m->colptr, (size_t)(C + 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&m->colptr, (size_t)(C + 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "colptr: %s", cudaGetErrorString(e)));
     DevBuf<int64_t> cnt;
     int rc = cnt.alloc(ctx, (size_t)C + 1);
@@ -377,8 +383,8 @@ extern "C" int bn_mat_synth_nb(bn_ctx *ctx, int64_t G, int64_t C, const double *
         return fail(bn_fail(ctx, BN_ERR_CUDA, "synth scan: %s", cudaGetErrorString(e)));
     if (nnz >= 4294967295LL) return fail(bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard"));
     m->nnz = nnz;
-    if ((e = cudaMalloc((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8)) != cudaSuccess)
+    if ((e = cudaMallocAsync((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_OOM, "matrix allocation failed: %s", cudaGetErrorString(e)));
     k_synth<true><<<grid, 256, 0, ctx->stream>>>(G, C, dmu.p, dsz.p, db.p, seed, gene0, nullptr, m->colptr, m->rowidx, m->val);
     ctx->launches++;

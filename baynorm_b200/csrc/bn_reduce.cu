@@ -133,6 +133,20 @@ extern "C" int bn_beta_default(bn_ctx *ctx, const bn_mat *m, double mean_beta, d
     return BN_OK;
 }
 
+template <bool PACKED>
+__device__ __forceinline__ void nz_load(const uint64_t *__restrict__ gm, const int32_t *__restrict__ cell,
+                                        const double *__restrict__ rval, int64_t k, int &c, double &x)
+{
+    if (PACKED) {
+        const uint64_t e = __ldcs(gm + k);
+        c = (int)(e >> 32);
+        x = (double)(uint32_t)e;
+    } else {
+        c = cell[k];
+        x = rval[k];
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // per-gene moments on the gene-major twin: one warp per gene.
 // mode 0: full EstPrior (MU, SIZE with NaN rule, V)     -- means computed here
@@ -141,8 +155,10 @@ extern "C" int bn_beta_default(bn_ctx *ctx, const bn_mat *m, double mean_beta, d
 // mode 3: as mode 0 but SIZE is the raw quotient m^2/(v-m) without the R-level NaN rule
 //         (what EstPrior_sprcpp / EstPrior_rcpp themselves return)
 // ---------------------------------------------------------------------------------
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_t C, const int64_t *__restrict__ rowptr,
-                                                     const int32_t *__restrict__ cell, const double *__restrict__ rval,
+                                                     const uint64_t *__restrict__ gm, const int32_t *__restrict__ cell,
+                                                     const double *__restrict__ rval,
                                                      const double *__restrict__ beta, const double *__restrict__ means_in,
                                                      double *__restrict__ MU, double *__restrict__ SIZE,
                                                      double *__restrict__ V)
@@ -159,8 +175,10 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
         } else {
             double s = 0.0;
             for (int64_t k = a + lane; k < b; k += 32) {
-                const double x = rval[k];
-                s += beta ? __ddiv_rn(x, __ldg(beta + cell[k])) : x;
+                double x;
+                int c;
+                nz_load<PACKED>(gm, cell, rval, k, c, x);
+                s += beta ? __ddiv_rn(x, __ldg(beta + c)) : x;
             }
             mean = __ddiv_rn(bn_warp_sum(s), n); // :1316-1318
             if (lane == 0 && MU) MU[g] = mean;
@@ -168,8 +186,10 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
         }
         double ss = 0.0;
         for (int64_t k = a + lane; k < b; k += 32) {
-            const double x = rval[k];
-            const double v = beta ? __ddiv_rn(x, __ldg(beta + cell[k])) : x;
+            double x;
+            int c;
+            nz_load<PACKED>(gm, cell, rval, k, c, x);
+            const double v = beta ? __ddiv_rn(x, __ldg(beta + c)) : x;
             const double d = __dsub_rn(v, mean);
             ss = __dadd_rn(ss, __dmul_rn(d, d)); // :1331
         }
@@ -196,7 +216,10 @@ static int launch_row_moments(bn_ctx *ctx, bn_mat *m, int mode, const double *be
 {
     BN_TRY(bn_mat_ensure_csr(ctx, m));
     const int blocks = (int)std::min<int64_t>((m->G + 7) / 8, 148 * 16);
-    BN_LAUNCH(ctx, k_row_moments, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->cell, m->rval, beta, means_in, MU, SIZE, V);
+    if (m->is_count)
+        BN_LAUNCH(ctx, k_row_moments<true>, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->gm, m->cell, m->rval, beta, means_in, MU, SIZE, V);
+    else
+        BN_LAUNCH(ctx, k_row_moments<false>, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->gm, m->cell, m->rval, beta, means_in, MU, SIZE, V);
     return BN_OK;
 }
 

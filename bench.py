@@ -52,7 +52,7 @@ CONFIGS = {
     0: dict(name="tiny smoke configuration", G=1500, C=800, m0=-0.675, out="mode", S=1, groups=1),
 }
 # FP64 pipe instructions per likelihood term, counted in the SASS of k_fit_size:
-FP64_PER_DENSE_TERM = 21     # table path of bn_log1p_pos incl. the product and the accumulate (11 on the series path)
+FP64_PER_DENSE_TERM = 3      # fma(r, beta, 1), multiply into the running product, 1/16 of a folded bn_log
 FP64_PER_NZ_TERM = 14        # fma(mu, beta, phi), bn_log, fma into the accumulator
 
 
