@@ -143,22 +143,6 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
                     __stcs(o + i, __dadd_rn(post_tempmu(xv, sz[e], m[e], b), xv));
                 } else if (MODE == POST_MODE) {
                     __stcs(o + i, post_mode(xv, sz[e], m[e], b));
-                } else {
-                    const double tm = post_tempmu(xv, sz[e], m[e], b);
-                    const double r = __dadd_rn(sz[e], xv);
-                    const NBParams P = bn_nb_setup(r, tm);
-                    Philox g;
-                    g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
-                    // one Philox counter block per 4 draws; sub-stream index = s / 4 so that the value
-                    // of draw s does not depend on S
-                    for (int s = 0; s < S; s++) {
-                        if ((s & 3) == 0) {
-                            g.c2 = (uint32_t)(s >> 2);
-                            g.c3 = 0;
-                            g.have = 0;
-                        }
-                        __stcs(o + i + sstride * s, bn_nb_draw(P, g) + xv);
-                    }
                 }
             }
         }
@@ -184,6 +168,153 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// 3-D draws (Main_NB_Bay, src/bayNorm_main.cpp:1063-1139): S draws x + NB(size+x, tempmu) per
+// gene x cell, out[i + G*(j + ncol*s)].
+//
+// Same tile walk as k_posterior (1024-gene tiles).  Per tile column:
+//   phase 1  every thread handles its 4 genes: NB parameters in FP64 (the reference's expression),
+//            then, if the mean is small (< SAMPLE_LIGHT_MAX: all x = 0 entries of ordinary genes,
+//            i.e. ~92 % of the matrix), S draws by single-uniform CDF inversion in float, stored
+//            straight to the S output planes (each store instruction writes 256 contiguous
+//            doubles); otherwise the gene is appended to the tile column's heavy list;
+//   phase 2  the heavy list x S is flattened over the CTA: each thread takes (entry, s) items and
+//            draws gamma-Poisson.  Light and heavy work never share a warp instruction, so a
+//            non-zero count does not stall 31 cheap lanes for hundreds of instructions.
+// Draw (gene, cell, s) is a pure function of (seed, global gene, global cell, s): light draws use
+// Philox block s/4 word s%4 of the element's stream, heavy draws their own sub-stream 2^31 + s.
+// ---------------------------------------------------------------------------------
+#define SAMPLE_EPT 4
+#define SAMPLE_TG (POST_THREADS * SAMPLE_EPT)
+#define SAMPLE_LIGHT_MAX 8.0
+
+struct HeavyEntry {
+    float r, M;
+    int gene; // local to the tile
+    float x;
+};
+
+__global__ void __launch_bounds__(POST_THREADS, 4)
+    k_post_sample(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                  const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
+                  const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
+                  int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
+{
+    __shared__ double xs[3][SAMPLE_TG];
+    __shared__ HeavyEntry heavy[SAMPLE_TG];
+    __shared__ int64_t s_lo[POST_NCMAX], s_end[POST_NCMAX];
+    __shared__ float inv_tab[64];
+    __shared__ int n_heavy[2]; // alternating per column so the reset never races with the next column's appends
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * SAMPLE_TG;
+    const int64_t tend = t0 + SAMPLE_TG;
+    const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
+    const int nc = (int)((jb + nc_per_cta < ncol ? jb + nc_per_cta : ncol) - jb);
+    if (tid < nc) {
+        const int64_t j = col0 + jb + tid;
+        const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
+        s_lo[tid] = (t0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, t0);
+        s_end[tid] = ce;
+    }
+    if (tid < 64) inv_tab[tid] = 1.0f / (float)(tid + 1);
+    if (tid == 0) n_heavy[0] = n_heavy[1] = 0;
+    double sz[SAMPLE_EPT], m[SAMPLE_EPT];
+#pragma unroll
+    for (int e = 0; e < SAMPLE_EPT; e++) {
+        const int64_t i = t0 + e * POST_THREADS + tid;
+        sz[e] = (i < G) ? __ldg(size + i) : 1.0;
+        m[e] = (i < G) ? __ldg(mu + i) : 0.0;
+        xs[0][e * POST_THREADS + tid] = 0.0;
+        xs[1][e * POST_THREADS + tid] = 0.0;
+    }
+    __syncthreads();
+    for (int jj = 0; jj <= nc; jj++) {
+        double *xcur = xs[jj % 3], *xprev = xs[(jj + 2) % 3], *xnext = xs[(jj + 1) % 3];
+        int32_t pr[2];
+        double pv[2];
+        int64_t kbase = 0, kend = 0;
+        if (jj < nc) {
+            kbase = s_lo[jj];
+            kend = s_end[jj];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int64_t k = kbase + q * POST_THREADS + tid;
+                pr[q] = (k < kend) ? __ldg(rowidx + k) : 0x7fffffff;
+                pv[q] = (k < kend) ? __ldcs(val + k) : 0.0;
+            }
+        }
+        const int64_t jl = jb + jj - 1, j = col0 + jl;
+        double *o = out + G * jl;
+        if (jj > 0) { // phase 1 of column jj-1
+            const double b = __ldg(beta + j);
+#pragma unroll 1
+            for (int e = 0; e < SAMPLE_EPT; e++) {
+                const int64_t i = t0 + e * POST_THREADS + tid;
+                if (i >= G) continue;
+                const double xv = xprev[e * POST_THREADS + tid];
+                const double tm = post_tempmu(xv, sz[e], m[e], b);
+                const double r = __dadd_rn(sz[e], xv);
+                if (!(tm > 0.0)) { // rgamma(shape, scale = 0) = 0 -> rpois(0) = 0: the draw is x itself
+                    for (int s = 0; s < S; s++) __stcs(o + i + sstride * s, xv);
+                } else if (tm < SAMPLE_LIGHT_MAX) {
+                    const NBLightF P = bn_nb_light_setup((float)r, (float)tm);
+                    Philox g;
+                    g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
+                    for (int s0 = 0; s0 < S; s0 += 4) {
+                        g.c2 = (uint32_t)(s0 >> 2);
+                        g.c3 = 0;
+                        g.refill();
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (s0 + q < S) __stcs(o + i + sstride * (s0 + q), (double)bn_nb_light_draw(P, g.out[q], inv_tab) + xv);
+                    }
+                } else {
+                    const int slot = atomicAdd(&n_heavy[jj & 1], 1);
+                    HeavyEntry h;
+                    h.r = (float)r;
+                    h.M = (float)tm;
+                    h.gene = e * POST_THREADS + tid;
+                    h.x = (float)xv;
+                    heavy[slot] = h;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < SAMPLE_EPT; e++) xnext[e * POST_THREADS + tid] = 0.0;
+        if (jj < nc) {
+            bool more = true;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if ((int64_t)pr[q] < tend) xcur[pr[q] - t0] = pv[q];
+                else more = false;
+            }
+            if (more) {
+                for (int64_t k = kbase + 2 * POST_THREADS + tid; k < kend; k += POST_THREADS) {
+                    const int64_t r = __ldg(rowidx + k);
+                    if (r >= tend) break;
+                    xcur[r - t0] = __ldcs(val + k);
+                }
+            }
+        }
+        __syncthreads();
+        if (jj > 0) { // phase 2 of column jj-1: heavy entries x S, flattened over the CTA
+            const int nh = n_heavy[jj & 1];
+            const int items = nh * S;
+            for (int it = tid; it < items; it += POST_THREADS) {
+                const int s = it / nh, ent = it - s * nh;
+                const HeavyEntry h = heavy[ent];
+                const int64_t i = t0 + h.gene;
+                Philox g;
+                g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0x80000000u + (uint32_t)s);
+                // x may not be exactly representable in float for non-integer inputs: re-read it
+                __stcs(o + i + sstride * s, bn_nb_heavy_draw(h.r, h.M, g) + xprev[h.gene]);
+            }
+            __syncthreads();
+            if (tid == 0) n_heavy[jj & 1] = 0;
+        }
+    }
+}
+
 static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BETA_vec, const double *size,
                        const double *mu, int64_t col0, int64_t ncol, int S, uint64_t seed, double *out)
 {
@@ -199,6 +330,17 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     BN_TRY(mm.bind(ctx, mu, (size_t)m->G));
     DevOut<double> o;
     BN_TRY(o.bind(ctx, out, nout));
+    if (mode == POST_SAMPLE) {
+        const int64_t tiles_s = (m->G + SAMPLE_TG - 1) / SAMPLE_TG;
+        int ncs = POST_NCMAX;
+        while (ncs > 1 && tiles_s * ((ncol + ncs - 1) / ncs) < 148 * 8) ncs >>= 1;
+        if ((ncol + ncs - 1) / ncs > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
+        dim3 grid_s((unsigned)tiles_s, (unsigned)((ncol + ncs - 1) / ncs));
+        BN_LAUNCH(ctx, k_post_sample, grid_s, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p, col0, ncol,
+                  ncs, o.p, S, seed, m->gene0, m->cell0, m->G * ncol);
+        BN_TRY(o.commit(ctx));
+        return bn_sync(ctx);
+    }
     static int ept = 0;
     if (!ept) {
         const char *e = getenv("BN_POST_EPT");
@@ -221,12 +363,10 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     } while (0)
     if (ept == 8) {
         if (mode == POST_MEAN) POST_GO(POST_MEAN, 8);
-        else if (mode == POST_MODE) POST_GO(POST_MODE, 8);
-        else POST_GO(POST_SAMPLE, 8);
+        else POST_GO(POST_MODE, 8);
     } else {
         if (mode == POST_MEAN) POST_GO(POST_MEAN, 4);
-        else if (mode == POST_MODE) POST_GO(POST_MODE, 4);
-        else POST_GO(POST_SAMPLE, 4);
+        else POST_GO(POST_MODE, 4);
     }
 #undef POST_GO
     BN_TRY(o.commit(ctx));
