@@ -24,7 +24,6 @@
 
 #define POST_THREADS 256
 #define POST_NCMAX 64 // columns walked by one CTA
-#define POST_PF 4     // non-zeros per thread prefetched one column ahead (covers 1024 per tile column)
 
 enum { POST_MEAN = 0, POST_MODE = 1, POST_SAMPLE = 2 };
 
@@ -76,7 +75,9 @@ __device__ __forceinline__ int64_t lower_bound_row(const int32_t *__restrict__ r
 //   (2) computes and stores column jj-1 from tile (jj-1)%3 and zeroes tile (jj+1)%3,
 //   (3) scatters the prefetched non-zeros into tile jj%3 (zeroed one iteration earlier),
 // then one __syncthreads().  Global-load latency of (1) is covered by the arithmetic of (2).
-template <int MODE, int POST_EPT>
+// POST_PF: non-zeros per thread prefetched two columns ahead (2 covers 512 per tile column: sparse
+// single-cell matrices; 4 covers 1024: dense-ish matrices such as config 2)
+template <int MODE, int POST_EPT, int POST_PF>
 __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
     k_posterior(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                 const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
 {
     constexpr int POST_TG = POST_THREADS * POST_EPT;
     extern __shared__ double xs[]; // [3][POST_TG]
-    __shared__ int64_t s_lo[POST_NCMAX], s_end[POST_NCMAX];
+    __shared__ int64_t s_lo[POST_NCMAX + 2], s_end[POST_NCMAX + 2];
+    __shared__ double s_beta[POST_NCMAX];
     const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * POST_TG;
     const int64_t tend = t0 + POST_TG;
@@ -97,6 +99,10 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
         const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
         s_lo[tid] = (t0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, t0);
         s_end[tid] = ce;
+        s_beta[tid] = __ldg(beta + j);
+    } else if (tid < nc + 2) {
+        s_lo[tid] = 0; // empty slices past the chunk keep the pipeline code branch-free
+        s_end[tid] = 0;
     }
     double sz[POST_EPT], m[POST_EPT];
 #pragma unroll
@@ -111,61 +117,66 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
         xs[POST_TG + e * POST_THREADS + tid] = 0.0;
     }
     __syncthreads();
-    for (int jj = 0; jj <= nc; jj++) {
-        double *xcur = xs + (jj % 3) * POST_TG;           // scatter target (column jj)
-        double *xprev = xs + ((jj + 2) % 3) * POST_TG;    // compute source (column jj-1)
-        double *xnext = xs + ((jj + 1) % 3) * POST_TG;    // zeroed for column jj+1
-        // (1) prefetch column jj's slice
-        int32_t pr[POST_PF];
-        double pv[POST_PF];
-        int64_t kbase = 0, kend = 0;
-        if (jj < nc) {
-            kbase = s_lo[jj];
-            kend = s_end[jj];
-#pragma unroll
-            for (int q = 0; q < POST_PF; q++) {
-                const int64_t k = kbase + q * POST_THREADS + tid;
-                pr[q] = (k < kend) ? __ldg(rowidx + k) : 0x7fffffff;
-                pv[q] = (k < kend) ? __ldcs(val + k) : 0.0;
-            }
-        }
-        // (2) column jj-1
-        if (jj > 0) {
-            const int64_t jl = jb + jj - 1, j = col0 + jl;
-            const double b = __ldg(beta + j);
-            double *o = out + G * jl;
-#pragma unroll
-            for (int e = 0; e < POST_EPT; e++) {
-                const int64_t i = t0 + e * POST_THREADS + tid;
-                const double xv = xprev[e * POST_THREADS + tid];
-                if (i >= G) continue;
-                if (MODE == POST_MEAN) {
-                    __stcs(o + i, __dadd_rn(post_tempmu(xv, sz[e], m[e], b), xv));
-                } else if (MODE == POST_MODE) {
-                    __stcs(o + i, post_mode(xv, sz[e], m[e], b));
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < POST_EPT; e++) xnext[e * POST_THREADS + tid] = 0.0;
-        // (3) scatter column jj
-        if (jj < nc) {
-            bool more = true;
-#pragma unroll
-            for (int q = 0; q < POST_PF; q++) {
-                if ((int64_t)pr[q] < tend) xcur[pr[q] - t0] = pv[q];
-                else more = false;
-            }
-            if (more) { // dense tile column: the rest of the slice
-                for (int64_t k = kbase + POST_PF * POST_THREADS + tid; k < kend; k += POST_THREADS) {
-                    const int64_t r = __ldg(rowidx + k);
-                    if (r >= tend) break;
-                    xcur[r - t0] = __ldcs(val + k);
-                }
-            }
-        }
-        __syncthreads();
+    // register sets for the slices of two columns in flight (loaded one iteration before use)
+    int32_t prA[POST_PF], prB[POST_PF];
+    double pvA[POST_PF], pvB[POST_PF];
+#define POST_LOAD(PR, PV, COL)                                                           \
+    do {                                                                                 \
+        const int64_t kb_ = s_lo[COL], ke_ = s_end[COL];                                 \
+        _Pragma("unroll") for (int q = 0; q < POST_PF; q++)                              \
+        {                                                                                \
+            const int64_t k = kb_ + q * POST_THREADS + tid;                              \
+            PR[q] = (k < ke_) ? __ldg(rowidx + k) : 0x7fffffff;                          \
+            PV[q] = (k < ke_) ? __ldcs(val + k) : 0.0;                                   \
+        }                                                                                \
+    } while (0)
+    // one pipeline stage: load slice of column jj+1, compute column jj-1, zero tile jj+1, scatter column jj
+#define POST_STAGE(JJ, PR_USE, PV_USE, PR_LOAD, PV_LOAD)                                                 \
+    do {                                                                                                 \
+        const int jj = (JJ);                                                                             \
+        double *xcur = xs + (jj % 3) * POST_TG, *xprev = xs + ((jj + 2) % 3) * POST_TG,                  \
+               *xnext = xs + ((jj + 1) % 3) * POST_TG;                                                   \
+        POST_LOAD(PR_LOAD, PV_LOAD, jj + 1);                                                             \
+        if (jj > 0) {                                                                                    \
+            const int64_t jl = jb + jj - 1;                                                              \
+            const double b = s_beta[jj - 1];                                                             \
+            double *o = out + G * jl;                                                                    \
+            _Pragma("unroll") for (int e = 0; e < POST_EPT; e++)                                         \
+            {                                                                                            \
+                const int64_t i = t0 + e * POST_THREADS + tid;                                           \
+                const double xv = xprev[e * POST_THREADS + tid];                                         \
+                if (i < G) {                                                                             \
+                    if (MODE == POST_MEAN) __stcs(o + i, __dadd_rn(post_tempmu(xv, sz[e], m[e], b), xv)); \
+                    else __stcs(o + i, post_mode(xv, sz[e], m[e], b));                                   \
+                }                                                                                        \
+            }                                                                                            \
+        }                                                                                                \
+        _Pragma("unroll") for (int e = 0; e < POST_EPT; e++) xnext[e * POST_THREADS + tid] = 0.0;        \
+        if (jj < nc) {                                                                                   \
+            bool more = true;                                                                            \
+            _Pragma("unroll") for (int q = 0; q < POST_PF; q++)                                          \
+            {                                                                                            \
+                if ((int64_t)PR_USE[q] < tend) xcur[PR_USE[q] - t0] = PV_USE[q];                         \
+                else more = false;                                                                       \
+            }                                                                                            \
+            if (more) { /* dense tile column: the rest of the slice */                                   \
+                const int64_t ke_ = s_end[jj];                                                           \
+                for (int64_t k = s_lo[jj] + POST_PF * POST_THREADS + tid; k < ke_; k += POST_THREADS) {  \
+                    const int64_t r = __ldg(rowidx + k);                                                 \
+                    if (r >= tend) break;                                                                \
+                    xcur[r - t0] = __ldcs(val + k);                                                      \
+                }                                                                                        \
+            }                                                                                            \
+        }                                                                                                \
+        __syncthreads();                                                                                 \
+    } while (0)
+    POST_LOAD(prA, pvA, 0);
+    for (int j2 = 0; j2 <= nc; j2 += 2) {
+        POST_STAGE(j2, prA, pvA, prB, pvB);
+        if (j2 + 1 <= nc) POST_STAGE(j2 + 1, prB, pvB, prA, pvA);
     }
+#undef POST_STAGE
+#undef POST_LOAD
 }
 
 // ---------------------------------------------------------------------------------
@@ -355,11 +366,17 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     dim3 grid((unsigned)tiles, (unsigned)((ncol + nc - 1) / nc));
     const int64_t sstride = m->G * ncol;
     const size_t smem = 3 * (size_t)TG * sizeof(double);
-#define POST_GO(MODE_, EPT_)                                                                                         \
+    const bool dense = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+#define POST_GO2(MODE_, EPT_, PF_)                                                                                   \
     do {                                                                                                             \
-        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<MODE_, EPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        BN_LAUNCH(ctx, (k_posterior<MODE_, EPT_>), grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, \
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<MODE_, EPT_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        BN_LAUNCH(ctx, (k_posterior<MODE_, EPT_, PF_>), grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, \
                   mm.p, col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);                                  \
+    } while (0)
+#define POST_GO(MODE_, EPT_)                  \
+    do {                                      \
+        if (dense) POST_GO2(MODE_, EPT_, 4);  \
+        else POST_GO2(MODE_, EPT_, 2);        \
     } while (0)
     if (ept == 8) {
         if (mode == POST_MEAN) POST_GO(POST_MEAN, 8);
@@ -369,6 +386,7 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         else POST_GO(POST_MODE, 4);
     }
 #undef POST_GO
+#undef POST_GO2
     BN_TRY(o.commit(ctx));
     return bn_sync(ctx);
 }

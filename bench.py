@@ -49,6 +49,10 @@ CONFIGS = {
             G=33000, C=200000, m0=-0.675, out="mean", S=1, groups=8),
     5: dict(name="cfg5: synthetic sparse 33k x 1.3M gene-sharded GG end-to-end (mean + S=20 draws)",
             G=33000, C=1300000, m0=-0.675, out="sample", S=20, groups=1),
+    6: dict(name="profiling proxy: sparse 33k x 10k (~8% nnz), GG, 3D output S=20",
+            G=33000, C=10000, m0=-0.675, out="sample", S=20, groups=1),
+    7: dict(name="profiling proxy: sparse 33k x 20k (~8% nnz), GG, 2D mean",
+            G=33000, C=20000, m0=-0.675, out="mean", S=1, groups=1),
     0: dict(name="tiny smoke configuration", G=1500, C=800, m0=-0.675, out="mode", S=1, groups=1),
 }
 # FP64 pipe instructions per likelihood term, counted in the SASS of k_fit_size:

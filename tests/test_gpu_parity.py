@@ -533,3 +533,71 @@ def test_baynorm_conditions_ll_and_gg(bn, ctx, oracle, small):
         bn.bayNorm(X, BETA_vec=beta, mode_version=True, mean_version=True, ctx=ctx)
     with pytest.raises(ValueError, match="conditions vector"):
         bn.bayNorm(X, BETA_vec=beta, Conditions=cond[:10], ctx=ctx)
+
+
+# ------------------------------------------------------------------------ gene-sharded path
+def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
+    """Two gene shards, each with its own context and the all-reduce hook installed (two host threads
+    on one GPU; the hook is a barrier + reduce over the two device buffers).  BETA, MME, BB_SIZE are
+    bit-identical to the unsharded run, the adjusted size agrees to the last few ulps."""
+    import threading
+    torch = pytest.importorskip("torch")
+    from baynorm_b200 import dist
+    X = small["X"]
+    Mo = small["Mo"]
+    Mfull = bn.Check_input(X, ctx)
+    beta_full = bn.api._default_beta(Mfull)
+    full = bn.Prior_fun(Mfull, beta_full, verbose=False)
+    world = 2
+    bounds = dist.balanced_gene_blocks(np.diff(Mo.p[:1]).sum() + (X > 0).sum(axis=1), world, n_cells=Mo.C)
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+    errors = []
+
+    def make_hook(rank):
+        def hook(buf, count, dtype, op, stream):
+            t = torch.as_tensor(dist._CudaBuf(buf, count), device="cuda:0")
+            torch.cuda.synchronize()
+            slots[rank] = t
+            barrier.wait()
+            st = torch.stack([s.clone() for s in slots])
+            red = st.sum(0) if op == 0 else (st.min(0).values if op == 1 else st.max(0).values)
+            torch.cuda.synchronize()
+            barrier.wait()
+            t.copy_(red)
+            torch.cuda.synchronize()
+            barrier.wait()
+            return 0
+        return hook
+
+    def run(rank):
+        try:
+            c = bn.Context(0)
+            c.set_allreduce(make_hook(rank), rank, world)
+            g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
+            G, Cn, p, i, x = dist.split_csc_rows(Mo.G, Mo.C, Mo.p, Mo.i, Mo.x, g0, g1)
+            M = bn.DeviceMatrix.from_csc(c, G, Cn, p, i, x)
+            M.set_origin(gene0=g0)
+            beta = bn.api._default_beta(M)
+            P = bn.Prior_fun(M, beta, verbose=False)
+            results[rank] = (beta, P)
+            M.close()
+            c.close()
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errors, errors
+    for r in range(world):
+        assert np.array_equal(results[r][0], beta_full)
+    cat = lambda f: np.concatenate([f(results[r][1]) for r in range(world)])
+    assert np.array_equal(cat(lambda P: P["MME_prior"]["MME_MU"]), full["MME_prior"]["MME_MU"])
+    assert np.array_equal(cat(lambda P: P["MME_prior"]["MME_SIZE"]), full["MME_prior"]["MME_SIZE"])
+    assert np.array_equal(cat(lambda P: P["BB_prior"]["BB_SIZE"]), full["BB_prior"]["BB_SIZE"])
+    assert rel_err(cat(lambda P: P["MME_SIZE_adjust"]), full["MME_SIZE_adjust"]).max() < 1e-12
