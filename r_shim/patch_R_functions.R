@@ -1,0 +1,36 @@
+## R-side changes a maintainer makes so that BB_Fun / Prior_fun / bayNorm call the batched entries.
+## Signatures, defaults and return structures are unchanged (R/PRIOR_FUNCTIONS.R:380-384, :241-245,
+## R/bayNorm.r:120-129); `parallel` and `NCores` are accepted and ignored (the fit is one kernel launch).
+## Not executed in this repository (no R in the image).
+
+BB_Fun <- function(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec,
+                   MU_lower = 0.01, MU_upper = 500, SIZE_lower = 0.01, SIZE_upper = 30,
+                   parallel = FALSE, NCores = 5, FIX_MU = TRUE, GR = FALSE) {
+    Data <- Check_input(Data)
+    if (!FIX_MU) stop("FIX_MU = FALSE is not available in the B200 backend yet")
+    BB_parmat <- .Call("bnb_fit_size", Data, as.numeric(BETA_vec), as.numeric(INITIAL_MU_vec),
+                       as.numeric(INITIAL_SIZE_vec), SIZE_lower, SIZE_upper, GR, PACKAGE = "bayNorm")
+    names(BB_parmat) <- rownames(Data)
+    BB_parmat
+}
+
+Prior_fun <- function(Data, BETA_vec, parallel = TRUE, NCores = 5, FIX_MU = TRUE, GR = FALSE,
+                      BB_SIZE = TRUE, verbose = TRUE) {
+    Data <- Check_input(Data)
+    if (!FIX_MU) stop("FIX_MU = FALSE is not available in the B200 backend yet")
+    r <- .Call("bnb_prior", Data, as.numeric(BETA_vec), BB_SIZE, GR, PACKAGE = "bayNorm")
+    MME_prior <- data.frame(MME_MU = r[[1]], MME_SIZE = r[[2]], row.names = rownames(Data))
+    if (!BB_SIZE) return(list(MME_prior = MME_prior, BETA_vec = BETA_vec))
+    BB_prior <- cbind(BB_SIZE = r[[3]], MME_MU = r[[1]])
+    rownames(BB_prior) <- rownames(Data)
+    MME_SIZE_adjust <- r[[4]]
+    names(MME_SIZE_adjust) <- rownames(Data)
+    if (verbose) message("Prior estimation has completed!")
+    list(MME_prior = MME_prior, BB_prior = BB_prior, MME_SIZE_adjust = MME_SIZE_adjust, BETA_vec = BETA_vec)
+}
+
+## inside bayNorm(), replacing R/bayNorm.r:164-170:
+##     if (is.null(BETA_vec)) BETA_vec <- .Call("bnb_beta_default", Data, PACKAGE = "bayNorm")
+## Main_mean_NB_spBay keeps its name:
+Main_mean_NB_spBay <- function(Data, BETA_vec, size, mu, S, thres)
+    methods::as(Main_mean_NB_Bay(Data, BETA_vec, size, mu, S, thres), "dgCMatrix")
