@@ -197,13 +197,15 @@ __global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
 // ---------------------------------------------------------------------------------
 #define SAMPLE_EPT 4
 #define SAMPLE_TG (POST_THREADS * SAMPLE_EPT)
-#define SAMPLE_LIGHT_MAX 8.0
+#define SAMPLE_LIGHT_MAX 20.0f  // means above this never put enough mass on SAMPLE_K points
+#define SAMPLE_LIGHT_MASS 0.95f // mass the 16-point CDF must cover for the table path (the rest: sequential tail)
 
 struct HeavyEntry {
     float r, M;
     int gene; // local to the tile
-    float x;
 };
+#define SAMPLE_K 32 // support points in the per-element CDF table
+#define SAMPLE_SMEM_BYTES (3 * SAMPLE_TG * 8 + SAMPLE_TG * 12 + SAMPLE_K * POST_THREADS * 4)
 
 __global__ void __launch_bounds__(POST_THREADS, 4)
     k_post_sample(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
@@ -211,8 +213,10 @@ __global__ void __launch_bounds__(POST_THREADS, 4)
                   const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
                   int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
 {
-    __shared__ double xs[3][SAMPLE_TG];
-    __shared__ HeavyEntry heavy[SAMPLE_TG];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double(*xs)[SAMPLE_TG] = reinterpret_cast<double(*)[SAMPLE_TG]>(smem_raw);                      // [3][TG] count tiles
+    HeavyEntry *heavy = reinterpret_cast<HeavyEntry *>(smem_raw + 3 * SAMPLE_TG * 8);                // [TG]
+    float *cdf = reinterpret_cast<float *>(smem_raw + 3 * SAMPLE_TG * 8 + SAMPLE_TG * 12);           // [SAMPLE_K][threads]
     __shared__ int64_t s_lo[POST_NCMAX], s_end[POST_NCMAX];
     __shared__ float inv_tab[64];
     __shared__ int n_heavy[2]; // alternating per column so the reset never races with the next column's appends
@@ -267,8 +271,27 @@ __global__ void __launch_bounds__(POST_THREADS, 4)
                 const double r = __dadd_rn(sz[e], xv);
                 if (!(tm > 0.0)) { // rgamma(shape, scale = 0) = 0 -> rpois(0) = 0: the draw is x itself
                     for (int s = 0; s < S; s++) __stcs(o + i + sstride * s, xv);
-                } else if (tm < SAMPLE_LIGHT_MAX) {
-                    const NBLightF P = bn_nb_light_setup((float)r, (float)tm);
+                    continue;
+                }
+                // CDF of the first SAMPLE_K support points, built once per element and shared by its S draws
+                const float rf = (float)r, Mf = (float)tm;
+                float ctop = 0.0f, p = 0.0f;
+                if (Mf < SAMPLE_LIGHT_MAX) {
+                    const float q = Mf / (rf + Mf);
+                    p = __expf(-rf * log1pf(Mf / rf));
+                    ctop = p;
+                    cdf[0 * POST_THREADS + tid] = ctop;
+#pragma unroll
+                    for (int k = 1; k < SAMPLE_K; k++) {
+                        p *= q * (rf + (float)(k - 1)) * inv_tab[k - 1];
+                        ctop += p;
+                        cdf[k * POST_THREADS + tid] = ctop;
+                    }
+                }
+                if (ctop >= SAMPLE_LIGHT_MASS) {
+                    // light element: each draw is a branch-free 5-step search of the CDF table; a uniform
+                    // beyond it (probability < 5 %) continues the recurrence sequentially
+                    const float q = Mf / (rf + Mf);
                     Philox g;
                     g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0u);
                     for (int s0 = 0; s0 < S; s0 += 4) {
@@ -276,16 +299,32 @@ __global__ void __launch_bounds__(POST_THREADS, 4)
                         g.c3 = 0;
                         g.refill();
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (s0 + q < S) __stcs(o + i + sstride * (s0 + q), (double)bn_nb_light_draw(P, g.out[q], inv_tab) + xv);
+                        for (int w = 0; w < 4; w++) {
+                            if (s0 + w >= S) break;
+                            const float u = bn_u01f(g.out[w]);
+                            int k = (u > cdf[15 * POST_THREADS + tid]) ? 16 : 0;
+                            k += (u > cdf[(k + 7) * POST_THREADS + tid]) ? 8 : 0;
+                            k += (u > cdf[(k + 3) * POST_THREADS + tid]) ? 4 : 0;
+                            k += (u > cdf[(k + 1) * POST_THREADS + tid]) ? 2 : 0;
+                            k += (u > cdf[k * POST_THREADS + tid]) ? 1 : 0;
+                            if (k == SAMPLE_K - 1 && u > ctop) { // tail
+                                float pk = p, ck = ctop, kk = (float)(SAMPLE_K - 1);
+                                while (u > ck && pk >= 1e-12f && kk < 4096.0f) {
+                                    pk *= q * (rf + kk) / (kk + 1.0f);
+                                    ck += pk;
+                                    kk += 1.0f;
+                                }
+                                k = (int)kk;
+                            }
+                            __stcs(o + i + sstride * (s0 + w), (double)k + xv);
+                        }
                     }
                 } else {
                     const int slot = atomicAdd(&n_heavy[jj & 1], 1);
                     HeavyEntry h;
-                    h.r = (float)r;
-                    h.M = (float)tm;
+                    h.r = rf;
+                    h.M = Mf;
                     h.gene = e * POST_THREADS + tid;
-                    h.x = (float)xv;
                     heavy[slot] = h;
                 }
             }
@@ -347,7 +386,8 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         while (ncs > 1 && tiles_s * ((ncol + ncs - 1) / ncs) < 148 * 8) ncs >>= 1;
         if ((ncol + ncs - 1) / ncs > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
         dim3 grid_s((unsigned)tiles_s, (unsigned)((ncol + ncs - 1) / ncs));
-        BN_LAUNCH(ctx, k_post_sample, grid_s, POST_THREADS, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p, col0, ncol,
+        BN_CUDA(ctx, cudaFuncSetAttribute(k_post_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM_BYTES));
+        BN_LAUNCH(ctx, k_post_sample, grid_s, POST_THREADS, SAMPLE_SMEM_BYTES, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p, col0, ncol,
                   ncs, o.p, S, seed, m->gene0, m->cell0, m->G * ncol);
         BN_TRY(o.commit(ctx));
         return bn_sync(ctx);

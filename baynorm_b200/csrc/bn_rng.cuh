@@ -270,7 +270,12 @@ __device__ float bn_rgammaf(Philox &g, float a)
         const float u = bn_u01f(g.next());
         const float x2 = x * x;
         if (u < 1.0f - 0.0331f * x2 * x2) return d * v * boost;
-        if (log((double)u) < 0.5 * (double)x2 + (double)d * (1.0 - (double)v + log((double)v))) return d * v * boost;
+        // full test (reached ~4 % of the time): float unless d is so large that float rounding of
+        // d * (1 - v + log v) would move the acceptance probability by more than ~1e-5
+        bool acc;
+        if (d <= 256.0f) acc = logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v));
+        else acc = log((double)u) < 0.5 * (double)x2 + (double)d * (1.0 - (double)v + log((double)v));
+        if (acc) return d * v * boost;
     }
     return d * boost;
 }
@@ -295,9 +300,14 @@ __device__ float bn_rpoisf(Philox &g, float lam)
         const float k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
         if (us >= 0.07f && V <= vr) return k;
         if (k < 0.0f || (us < 0.013f && V > us)) continue;
-        const double dl = lam, dk = k;
-        if (log((double)V) + log((double)inv_alpha) - log((double)a / ((double)us * us) + b) <= -dl + dk * log(dl) - lgamma(dk + 1.0))
-            return k;
+        bool acc;
+        if (lam <= 256.0f) {
+            acc = logf(V * inv_alpha / (a / (us * us) + b)) <= -lam + k * logf(lam) - lgammaf(k + 1.0f);
+        } else {
+            const double dl = lam, dk = k;
+            acc = log((double)V) + log((double)inv_alpha) - log((double)a / ((double)us * us) + b) <= -dl + dk * log(dl) - lgamma(dk + 1.0);
+        }
+        if (acc) return k;
     }
     return floorf(lam);
 }

@@ -486,21 +486,22 @@ def main():
     return 0
 
 
-def _auto_samples(args, G, C):
-    # ~10-30 s of CPU work: the fit costs ~30 evaluations x C cells x ~60 ns per gene
-    per_gene = 30 * C * 60e-9
+def _auto_samples(args, G, C, rho=0.08, S=1, out_kind="mode"):
+    """Bounded CPU sample, ~10-20 s of fit + a few seconds of posterior on this box's cores.  Measured
+    on the oracle: ~60 ns per zero cell and ~450 ns per non-zero per likelihood evaluation (dnbinom_mu's
+    saddle-point branch), ~30 evaluations per gene; 7 ns per posterior mean/mode element, ~80 ns per draw."""
     threads = os.cpu_count() or 1
-    gs = args.cpu_genes or int(max(threads, min(G, 12.0 * threads / per_gene)))
-    cs = args.cpu_cols or int(max(1, min(C, 4.0 / (G * 12e-9))))
+    per_gene = 30.0 * C * (60e-9 + 450e-9 * rho)
+    gs = args.cpu_genes or int(max(threads, min(G, 15.0 * threads / per_gene)))
+    per_col = G * (7e-9 if out_kind != "sample" else 80e-9 * S)
+    cs = args.cpu_cols or int(max(1, min(C, 4.0 / per_col)))
     return gs, cs, threads
 
 
 def cpu_baseline_block(args, cfg, M, G, C, S, out_kind):
     from oracle import oracle as O
     O.build()
-    gs, cs, threads = _auto_samples(args, G, C)
-    if out_kind == "sample":
-        cs = max(1, cs // S)
+    gs, cs, threads = _auto_samples(args, G, C, M.nnz / float(G * C), S, out_kind)
     r = cpu_reference(args, cfg, G, C, S, out_kind, M.export_csc(), gs, cs, threads)
     total_elements = G * C * S
     return {"value": total_elements / r["seconds_full_extrapolated"], "unit": "posterior elements/s",
@@ -519,9 +520,7 @@ def main_reference(args, cfg):
     G, C, S, out_kind = cfg["G"], cfg["C"], cfg["S"], cfg["out"]
     # the sample must be the same workload: generate the same synthetic matrix on the GPU if there is
     # one (it is only the data source here), else a numpy NB draw of a gene block
-    gs, cs, threads = _auto_samples(args, G, C)
-    if out_kind == "sample":
-        cs = max(1, cs // S)
+    gs, cs, threads = _auto_samples(args, G, C, 0.5 if cfg["m0"] > 0 else 0.08, S, out_kind)
     csc = None
     try:
         import baynorm_b200 as bn
