@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(POST_THREADS, 4)
                             k += (u > cdf[k * POST_THREADS + tid]) ? 1 : 0;
                             if (k == SAMPLE_K - 1 && u > ctop) { // tail
                                 float pk = p, ck = ctop, kk = (float)(SAMPLE_K - 1);
-                                while (u > ck && pk >= 1e-12f && kk < 4096.0f) {
+                                // stop once p(k) no longer moves the float CDF: u then lies in the last ~1e-7 of
+                                // mass and k is already at that quantile
+                                while (u > ck && pk > ck * 3e-8f && kk < 4096.0f) {
                                     pk *= q * (rf + kk) / (kk + 1.0f);
                                     ck += pk;
                                     kk += 1.0f;
