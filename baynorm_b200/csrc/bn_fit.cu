@@ -18,6 +18,7 @@
 // each evaluation is a group-wide FP64 reduction with a fixed summation order, so a gene's
 // result does not depend on which group ran it, on the grid size or on the GPU count.
 #include <math.h>
+#include <stdlib.h>
 
 #include "bn_internal.cuh"
 #include "bn_math.cuh"
@@ -526,6 +527,228 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Multi-slot variant for long genes (C >= 8192): one 256-thread CTA evaluates FIT_NS genes
+// ("slots") per sweep over the cells, each at its own trial size.  Every beta_j fetched from
+// L1/L2 feeds FIT_NS likelihoods, which is what bounds the single-slot kernel at 1e5+ cells (each
+// evaluation streams the whole beta vector; 33k genes x 26 evaluations x 0.8 MB = 680 GB of L2
+// traffic for config 3).  Slots are independent state machines in shared memory: a slot that
+// converges pops the next gene from the queue while the others continue, so no slot idles until the
+// queue is empty.  After a sweep, thread s steps the solver of slot s (the FIT_NS state machines
+// run as lanes of one warp).  A gene's result is a pure function of its own data: summation order,
+// fold points and solver path do not depend on which genes share the CTA.
+// ---------------------------------------------------------------------------------
+#define FIT_NS 4
+
+struct FitSlot {
+    const uint64_t *nz;
+    int64_t nnz, gene;
+    double mu, Kc, next;
+    int kmax, n_big, nfe, state; // state: 0 idle, 1 fresh (needs prologue), 2 running
+    SpgState spg;
+    BrentState brent;
+    uint32_t tail[FitCfg<256>::HMAX + 1];
+};
+
+__global__ void __launch_bounds__(256, 3)
+    k_fit_size_ms(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
+                  const double *__restrict__ beta, const double *__restrict__ logbeta, const double *__restrict__ mu0,
+                  const double *__restrict__ size0, double lower, double upper, double beta_max, FitOpts o,
+                  unsigned long long *__restrict__ queue, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
+                  int32_t *__restrict__ nfe_out)
+{
+    constexpr int HMAX = FitCfg<256>::HMAX;
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    __shared__ FitSlot slot[FIT_NS];
+    __shared__ double scratch[FIT_NS][8];
+    __shared__ double red8[8];
+    __shared__ int xmax_sh, n_running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bn_log_table_load(tab);
+    if (tid < FIT_NS) slot[tid].state = 0;
+    __syncthreads();
+    for (;;) {
+        // ---- refill idle slots (thread 0); all-zero genes are answered on the spot -------------
+        if (tid == 0) {
+            int running = 0;
+            for (int s = 0; s < FIT_NS; s++) {
+                FitSlot &sl = slot[s];
+                while (sl.state == 0) {
+                    const unsigned long long gq = atomicAdd(queue, 1ULL);
+                    if (gq >= (unsigned long long)G) break;
+                    const int64_t gi = (int64_t)gq, a = rowptr[gi], n = rowptr[gi + 1] - a;
+                    const double mu = mu0[gi];
+                    if (n == 0 || !(mu > 0.0)) { // flat likelihood: spg returns the projected start
+                        size_out[gi] = proj(size0[gi], lower, upper);
+                        if (conv_out) conv_out[gi] = 0;
+                        if (nfe_out) nfe_out[gi] = (o.method == BN_FIT_SPG) ? 2 : 0;
+                        continue;
+                    }
+                    sl.nz = gm + a;
+                    sl.nnz = n;
+                    sl.gene = gi;
+                    sl.mu = mu;
+                    sl.nfe = 0;
+                    sl.state = 1;
+                }
+                running += (sl.state != 0);
+            }
+            n_running = running;
+        }
+        __syncthreads();
+        if (n_running == 0) break;
+        // ---- prologue of fresh slots: count histogram -> tail table, Kc, largest count ---------
+        for (int s = 0; s < FIT_NS; s++) {
+            FitSlot &sl = slot[s];
+            if (sl.state != 1) continue; // uniform
+            for (int q = tid; q <= HMAX; q += 256) sl.tail[q] = 0;
+            if (tid == 0) xmax_sh = 0;
+            __syncthreads();
+            const double lmu = log(sl.mu);
+            double kk = 0.0;
+            int xm = 0;
+            for (int64_t k = tid; k < sl.nnz; k += 256) {
+                const uint64_t e0 = __ldg(sl.nz + k);
+                const double x = (double)(uint32_t)e0;
+                kk += x * (lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
+                const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
+                atomicAdd(&sl.tail[xi - 1], 1u);
+                xm = max(xm, xi);
+            }
+            atomicMax(&xmax_sh, xm);
+            const double Kc = bn_group_sum<256>(kk, red8);
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = sl.tail[HMAX];
+                sl.n_big = (int)run;
+                for (int q = HMAX - 1; q >= 0; q--) {
+                    run += sl.tail[q];
+                    sl.tail[q] = run;
+                }
+                sl.Kc = Kc;
+                sl.kmax = min(HMAX, xmax_sh);
+                if (o.method == BN_FIT_BRENT) {
+                    sl.brent.init(lower, upper);
+                    sl.next = sl.brent.next;
+                } else {
+                    sl.spg.init(size0[sl.gene], lower, upper, o);
+                    sl.next = sl.spg.next;
+                }
+                sl.state = 2;
+            }
+            __syncthreads();
+        }
+        // ---- one sweep: l(next) of every running slot ------------------------------------------
+        double r[FIT_NS], pa[FIT_NS], pb[FIT_NS], acc[FIT_NS];
+        bool any_slow = false;
+#pragma unroll
+        for (int s = 0; s < FIT_NS; s++) {
+            r[s] = (slot[s].state == 2) ? slot[s].mu / slot[s].next : 0.0;
+            pa[s] = 1.0;
+            pb[s] = 1.0;
+            acc[s] = 0.0;
+            any_slow |= !(fma(r[s], beta_max, 1.0) < 9.0e18); // (1 + r beta_max)^16 must stay finite
+        }
+        if (!any_slow) {
+            // blocks of 16 x 512 cells: 32 factors per slot between folds, no branch inside the block
+            int64_t j = tid;
+            for (; j + 15 * 512 + 256 < C; j += 16 * 512) {
+#pragma unroll 4
+                for (int it = 0; it < 16; it++) {
+                    const double b0 = __ldg(beta + j + it * 512), b1 = __ldg(beta + j + it * 512 + 256);
+#pragma unroll
+                    for (int s = 0; s < FIT_NS; s++) {
+                        pa[s] *= fma(r[s], b0, 1.0);
+                        pb[s] *= fma(r[s], b1, 1.0);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < FIT_NS; s++) {
+                    acc[s] += bn_log(pa[s], tab) + bn_log(pb[s], tab);
+                    pa[s] = 1.0;
+                    pb[s] = 1.0;
+                }
+            }
+            for (; j < C; j += 256) { // fewer than 32 factors left per thread
+                const double b0 = __ldg(beta + j);
+#pragma unroll
+                for (int s = 0; s < FIT_NS; s++) pa[s] *= fma(r[s], b0, 1.0);
+            }
+        } else { // absurd mu/size ratios: one logarithm per cell keeps everything finite
+            for (int64_t j = tid; j < C; j += 256) {
+                const double b0 = __ldg(beta + j);
+#pragma unroll
+                for (int s = 0; s < FIT_NS; s++) acc[s] += bn_log(fma(r[s], b0, 1.0), tab);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < FIT_NS; s++) acc[s] += bn_log(pa[s], tab) + bn_log(pb[s], tab);
+#pragma unroll 1
+        for (int s = 0; s < FIT_NS; s++) {
+            const FitSlot &sl = slot[s];
+            if (sl.state != 2) continue; // uniform
+            const double phi = sl.next, mu = sl.mu;
+            double t = -phi * acc[s];
+            double s0 = 0.0, s1 = 0.0;
+            const uint64_t *__restrict__ nz = sl.nz;
+            const int64_t nnz = sl.nnz;
+            int64_t k = tid;
+            for (; k + 3 * 256 < nnz; k += 4 * 256) {
+                const uint64_t e0 = __ldg(nz + k), e1 = __ldg(nz + k + 256), e2 = __ldg(nz + k + 512), e3 = __ldg(nz + k + 768);
+                const double b0 = __ldg(beta + (e0 >> 32)), b1 = __ldg(beta + (e1 >> 32)), b2 = __ldg(beta + (e2 >> 32)),
+                             b3 = __ldg(beta + (e3 >> 32));
+                s0 = fma(-(double)(uint32_t)e0, bn_log(fma(mu, b0, phi), tab), s0);
+                s1 = fma(-(double)(uint32_t)e1, bn_log(fma(mu, b1, phi), tab), s1);
+                s0 = fma(-(double)(uint32_t)e2, bn_log(fma(mu, b2, phi), tab), s0);
+                s1 = fma(-(double)(uint32_t)e3, bn_log(fma(mu, b3, phi), tab), s1);
+            }
+            for (; k < nnz; k += 256) {
+                const uint64_t e0 = __ldg(nz + k);
+                s0 = fma(-(double)(uint32_t)e0, bn_log(fma(mu, __ldg(beta + (e0 >> 32)), phi), tab), s0);
+            }
+            if (sl.n_big != 0) {
+                const double lgref = bn_lgamma_stirling(phi + (double)HMAX, tab);
+                for (k = tid; k < nnz; k += 256) {
+                    const double x = (double)(uint32_t)__ldg(nz + k);
+                    if (x > (double)HMAX) s1 += bn_lgamma_stirling(x + phi, tab) - lgref;
+                }
+            }
+            for (int q = tid; q < sl.kmax; q += 256) s1 = fma((double)sl.tail[q], bn_log(phi + (double)q, tab), s1);
+            t += s0 + s1;
+            t = bn_warp_sum(t);
+            if (lane == 0) scratch[s][warp] = t;
+        }
+        __syncthreads();
+        // ---- thread s steps the solver of slot s ------------------------------------------------
+        if (tid < FIT_NS && slot[tid].state == 2) {
+            FitSlot &sl = slot[tid];
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += scratch[tid][w];
+            const double val = -(tot + sl.Kc);
+            sl.nfe++;
+            bool more;
+            int conv;
+            if (o.method == BN_FIT_BRENT) {
+                more = sl.brent.step(val, o);
+                sl.next = sl.brent.next;
+                conv = sl.brent.conv;
+            } else {
+                more = sl.spg.step(val, o);
+                sl.next = sl.spg.next;
+                conv = sl.spg.conv;
+            }
+            if (!more) {
+                size_out[sl.gene] = sl.next;
+                if (conv_out) conv_out[sl.gene] = conv;
+                if (nfe_out) nfe_out[sl.gene] = sl.nfe;
+                sl.state = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // largest beta (decides between the series and the table form of log1p per evaluation)
 __global__ void __launch_bounds__(1024) k_max_vec(int64_t n, const double *__restrict__ v, double *__restrict__ out)
 {
@@ -602,8 +825,11 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
         const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);
+        static int single = -1;
+        if (single < 0) single = getenv("BN_FIT_SINGLE_SLOT") ? 1 : 0; // A/B switch for profiling
         if (grad) BN_LAUNCH(ctx, (k_fit_size<256, true>), grid, 256, 0, FIT_ARGS);
-        else BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
+        else if (single) BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
+        else BN_LAUNCH(ctx, k_fit_size_ms, (int)std::min<int64_t>((m->G + FIT_NS - 1) / FIT_NS, (int64_t)sms * 3), 256, 0, FIT_ARGS);
     } else {
         const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 24);
         if (grad) BN_LAUNCH(ctx, (k_fit_size<32, true>), grid, 128, 0, FIT_ARGS);
