@@ -37,7 +37,7 @@ __device__ __forceinline__ double post_tempmu(double x, double size, double mu, 
 //   reference:  floor( ((x+size)*(mu-mu*beta)/(size+mu*beta)) / (size+x) * ((size+x)-1) ) + x
 // The two IEEE divisions dominate the FP64 cost of the kernel, and floor() only needs to know on
 // which side of an integer the value lies.  Fast path: the same real-number quantity with ONE
-// approximate reciprocal (rcp.approx seed + one Newton step, relative error < 2^-44 overall);
+// approximate reciprocal (rcp.approx seed + two Newton steps, relative error < 2^-50 overall);
 // if an integer lies within 2^-42 * v of it, redo the reference sequence exactly.  The fast value
 // and the reference value both differ from the real number by far less than that margin, so
 // whenever the fast path is taken floor() of both is the same integer.
@@ -50,6 +50,7 @@ __device__ __forceinline__ double post_mode(double x, double size, double mu, do
     // in real arithmetic the (size+x) factors cancel: v = (mu - mu*beta) * (size+x-1) / (size + mu*beta)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    y = fma(y, fma(-den, y, 1.0), y); // rcp.approx is good to ~2^-20: two Newton steps reach full precision
     y = fma(y, fma(-den, y, 1.0), y);
     const double v = (a * rm1) * y;
     const double fl = floor(v);

@@ -601,3 +601,88 @@ def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
     assert np.array_equal(cat(lambda P: P["MME_prior"]["MME_SIZE"]), full["MME_prior"]["MME_SIZE"])
     assert np.array_equal(cat(lambda P: P["BB_prior"]["BB_SIZE"]), full["BB_prior"]["BB_SIZE"])
     assert rel_err(cat(lambda P: P["MME_SIZE_adjust"]), full["MME_SIZE_adjust"]).max() < 1e-12
+
+
+# ------------------------------------------------------------------------ edge cases
+def test_large_counts_go_through_stirling(bn, ctx, oracle):
+    """Counts above the tail table (64 for warp groups, 256 for CTA groups) use Stirling's series;
+    the likelihood fit must still agree with the oracle.  C = 9000 selects the multi-slot CTA kernel."""
+    rng = np.random.default_rng(4)
+    for C in (300, 9000):
+        G = 24
+        beta = np.clip(rng.lognormal(0, 0.4, C) * 0.06, 0.005, 0.5)
+        mu = np.array([2000.0, 9000.0, 300.0, 4000.0] * 6)[:G] * rng.uniform(0.8, 1.2, G)
+        size = rng.lognormal(0.5, 0.5, G)
+        lam = rng.gamma(size[:, None], (mu[:, None] * beta[None, :]) / size[:, None])
+        X = rng.poisson(lam).astype(np.float64)
+        assert X.max() > 300
+        Mo = oracle.CSC.from_dense(X)
+        Po = oracle.Prior_fun(Mo, beta, BB_SIZE=False)
+        mu0, s0 = Po["MME_prior"]["MME_MU"], Po["MME_prior"]["MME_SIZE"]
+        lo, hi = float(s0.min()), float(np.ceil(s0.max()))
+        want = oracle.BB_Fun(Mo, beta, mu0, s0, lo, hi, nthreads=8)
+        got = bn.BB_Fun(bn.Check_input(X, ctx), beta, mu0, s0, SIZE_lower=lo, SIZE_upper=hi)
+        assert np.median(rel_err(got, want)) < 1e-6 and rel_err(got, want).max() < 2e-4
+        g = 1
+        f_gpu = bn.MarginalF_NB_1D(got[g], mu0[g], X[g], beta, ctx=ctx)
+        f_cpu = oracle.MarginalF_NB_1D(got[g], mu0[g], X[g], beta)
+        assert abs(f_gpu - f_cpu) <= 1e-11 * abs(f_cpu)
+
+
+def test_ragged_shapes_and_empty_columns(bn, ctx, oracle):
+    """One gene, one cell, tile boundaries +-1, all-zero matrix columns and rows."""
+    rng = np.random.default_rng(6)
+    for G, C in ((1, 5), (7, 1), (2049, 3), (1023, 65), (1025, 130)):
+        X = rng.poisson(0.3, (G, C)).astype(np.float64)
+        X[:, C // 2] = 0
+        X[G // 2, :] = 0
+        beta = rng.uniform(0.02, 0.4, C)
+        size = rng.uniform(0.2, 4, G)
+        mu = rng.uniform(0.0, 6, G)
+        mu[0] = 0.0
+        Mo = oracle.CSC.from_dense(X)
+        M = bn.Check_input(X, ctx)
+        assert np.array_equal(bn.Main_mode_NB_Bay(M, beta, size, mu), oracle.Main_mode_NB_Bay(Mo, beta, size, mu))
+        assert np.array_equal(bn.Main_mean_NB_Bay(M, beta, size, mu), oracle.Main_mean_NB_Bay(Mo, beta, size, mu))
+        d = bn.Main_NB_Bay(M, beta, size, mu, S=3, seed=1)
+        assert d.shape == (G, C, 3) and (d >= X[:, :, None]).all()
+        assert (d[0] == X[0][:, None]).all()                       # mu = 0: the draw is x itself
+    Z = np.zeros((5, 4))
+    Mz = bn.Check_input(Z, ctx)
+    assert Mz.nnz == 0
+    assert np.array_equal(bn.Main_mean_NB_Bay(Mz, np.full(4, 0.1), np.ones(5), np.ones(5)),
+                          oracle.Main_mean_NB_Bay(oracle.CSC.from_dense(Z), np.full(4, 0.1), np.ones(5), np.ones(5)))
+    with pytest.raises(bn.BayNormError):
+        bn.api._default_beta(Mz)                                    # all column sums zero: no beta in (0,1)
+    with pytest.raises(bn.BayNormError):
+        bn.Prior_fun(bn.Check_input(np.ones((3, 1)), ctx), np.array([0.1]), verbose=False)   # MME needs >= 2 cells
+
+
+def test_posterior_on_non_integer_data(bn, ctx, oracle, small):
+    """The posterior closed forms accept any non-negative doubles (e.g. UMI_sffl-scaled data)."""
+    X = small["X"][:50, :40] * 0.37
+    beta, size, mu = small["beta"][:40], small["size"][:50], small["mu"][:50]
+    Mo = oracle.CSC.from_dense(X)
+    M = bn.Check_input(X, ctx)
+    assert not M.is_count
+    assert np.array_equal(bn.Main_mean_NB_Bay(M, beta, size, mu), oracle.Main_mean_NB_Bay(Mo, beta, size, mu))
+    assert np.array_equal(bn.Main_mode_NB_Bay(M, beta, size, mu), oracle.Main_mode_NB_Bay(Mo, beta, size, mu))
+    pri = bn.EstPrior(M, verbose=False)
+    w = oracle.EstPrior(Mo, None)
+    assert rel_err(pri["MU"], w["MU"]).max() < 1e-13
+
+
+def test_mode_exact_fallback_near_integers(bn, ctx, oracle):
+    """Parameters chosen so that (mu - mu*beta)(size+x-1)/(size+mu*beta) is an exact or near integer:
+    the fast reciprocal path must hand over to the exact IEEE sequence."""
+    G, C = 64, 33
+    size = np.full(G, 3.0)
+    mu = np.arange(1, G + 1, dtype=np.float64)
+    beta = np.full(C, 0.5)                       # v = (mu/2)(2 + x)/(3 + mu/2): many exact rationals
+    X = np.tile(np.arange(C, dtype=np.float64) % 5, (G, 1))
+    size[::3] = 2.0
+    beta[::4] = 0.25
+    Mo = oracle.CSC.from_dense(X)
+    got = bn.Main_mode_NB_Bay(bn.Check_input(X, ctx), beta, size, mu)
+    assert np.array_equal(got, oracle.Main_mode_NB_Bay(Mo, beta, size, mu))
+    assert np.array_equal(got, oracle.np_post_mode(X, beta, size, mu))
