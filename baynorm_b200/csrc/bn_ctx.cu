@@ -57,6 +57,7 @@ int bn_ctx_create(int device, bn_ctx **out)
         return bn_fail(nullptr, BN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
+    cudaHostAlloc((void **)&c->pinned, 64 * sizeof(double), cudaHostAllocDefault);
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -75,6 +76,7 @@ void bn_ctx_destroy(bn_ctx *ctx)
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
 }
 

@@ -418,10 +418,11 @@ template <int TPG, bool GRAD>
 __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
     k_fit_size(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
                const double *__restrict__ beta, const double *__restrict__ logbeta,
-               const double *__restrict__ mu0, const double *__restrict__ size0, double lower, double upper,
-               double beta_max, FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
+               const double *__restrict__ mu0, const double *__restrict__ size0, const double *__restrict__ params,
+               FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
                int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
 {
+    const double lower = params[0], upper = params[1], beta_max = params[2]; // device-resident: no host round trip
     constexpr int NGROUP = (TPG == 32) ? 4 : 1;
     constexpr int HMAX = FitCfg<TPG>::HMAX;
     __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
@@ -553,10 +554,11 @@ struct FitSlot {
 __global__ void __launch_bounds__(256, 3)
     k_fit_size_ms(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
                   const double *__restrict__ beta, const double *__restrict__ logbeta, const double *__restrict__ mu0,
-                  const double *__restrict__ size0, double lower, double upper, double beta_max, FitOpts o,
+                  const double *__restrict__ size0, const double *__restrict__ params, FitOpts o,
                   unsigned long long *__restrict__ queue, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
                   int32_t *__restrict__ nfe_out)
 {
+    const double lower = params[0], upper = params[1], beta_max = params[2]; // device-resident: no host round trip
     constexpr int HMAX = FitCfg<256>::HMAX;
     __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
     __shared__ FitSlot slot[FIT_NS];
@@ -785,14 +787,23 @@ extern "C" void bn_fit_opts_default(bn_fit_opts *o)
     o->reserved = 0;
 }
 
-// device-pointer core shared by bn_fit_size and bn_prior.  lower/upper are host scalars.
+// params[0..1] = box: either the host scalars, or (from_mm) derived on the device from
+// mm = {min, -max} of the MME sizes: lower = min, upper = ceiling(max)  (R/PRIOR_FUNCTIONS.R:277-279)
+__global__ void k_fit_params(double lower, double upper, const double *__restrict__ mm, double *__restrict__ params)
+{
+    params[0] = mm ? mm[0] : lower;
+    params[1] = mm ? ceil(-mm[1]) : upper;
+}
+
+// device-pointer core shared by bn_fit_size and bn_prior.  The box is (lower, upper) or, when d_mm
+// is given, read from device memory so that bn_prior never waits for the host between stages.
 int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const double *d_mu0, const double *d_size0,
-                       double lower, double upper, const bn_fit_opts *opts, double *d_size_out, int32_t *d_conv,
-                       int32_t *d_nfe)
+                       double lower, double upper, const double *d_mm, const bn_fit_opts *opts, double *d_size_out,
+                       int32_t *d_conv, int32_t *d_nfe)
 {
     if (!m->is_count)
         return bn_fail(ctx, BN_ERR_NONCOUNT, "the likelihood fit needs non-negative integer counts (dnbinom_mu is 0 elsewhere)");
-    if (!(lower > 0.0) || !(upper >= lower)) return bn_fail(ctx, BN_ERR_INVALID, "bad size bounds [%g, %g]", lower, upper);
+    if (!d_mm && (!(lower > 0.0) || !(upper >= lower))) return bn_fail(ctx, BN_ERR_INVALID, "bad size bounds [%g, %g]", lower, upper);
     bn_fit_opts od;
     bn_fit_opts_default(&od);
     if (opts) od = *opts;
@@ -813,15 +824,13 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     DevBuf<unsigned long long> q;
     BN_TRY(q.alloc(ctx, 1));
     BN_CUDA(ctx, cudaMemsetAsync(q.p, 0, 8, ctx->stream));
-    DevBuf<double> bmax;
-    BN_TRY(bmax.alloc(ctx, 1));
-    BN_LAUNCH(ctx, k_max_vec, 1, 1024, 0, m->C, d_beta, bmax.p);
-    double beta_max = 1.0;
-    BN_CUDA(ctx, cudaMemcpyAsync(&beta_max, bmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    BN_TRY(bn_sync(ctx));
+    DevBuf<double> params;
+    BN_TRY(params.alloc(ctx, 4));
+    BN_LAUNCH(ctx, k_fit_params, 1, 1, 0, lower, upper, d_mm, params.p);
+    BN_LAUNCH(ctx, k_max_vec, 1, 1024, 0, m->C, d_beta, params.p + 2);
     const int sms = ctx->prop.multiProcessorCount;
     const bool grad = o.use_gradient != 0;
-#define FIT_ARGS m->G, m->C, m->rowptr, m->gm, d_beta, lb.p, d_mu0, d_size0, lower, upper, beta_max, o, q.p, d_size_out, d_conv, d_nfe
+#define FIT_ARGS m->G, m->C, m->rowptr, m->gm, d_beta, lb.p, d_mu0, d_size0, params.p, o, q.p, d_size_out, d_conv, d_nfe
     if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
         const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);
@@ -855,7 +864,7 @@ extern "C" int bn_fit_size(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const
     BN_TRY(so.bind(ctx, size_out, (size_t)m->G));
     BN_TRY(co.bind(ctx, conv, (size_t)m->G));
     BN_TRY(no.bind(ctx, nfeval, (size_t)m->G));
-    BN_TRY(bn_fit_size_device(ctx, m, b.p, mu0.p, s0.p, SIZE_lower, SIZE_upper, opts, so.p, co.p, no.p));
+    BN_TRY(bn_fit_size_device(ctx, m, b.p, mu0.p, s0.p, SIZE_lower, SIZE_upper, nullptr, opts, so.p, co.p, no.p));
     BN_TRY(so.commit(ctx));
     BN_TRY(co.commit(ctx));
     BN_TRY(no.commit(ctx));

@@ -22,6 +22,7 @@ struct bn_ctx {
     void *ar_user = nullptr;
     int rank = 0, world = 1;
     cudaEvent_t ev[8] = {};
+    double *pinned = nullptr; // 64 doubles of page-locked host memory for truly asynchronous scalar read-backs
 };
 
 struct bn_mat {

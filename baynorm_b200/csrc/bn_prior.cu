@@ -11,8 +11,8 @@ int bn_mme_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, double *d_MU, do
 int bn_size_bounds_device(bn_ctx *ctx, int64_t G, double *d_size, double *d_mm);
 int bn_adjust_size_device(bn_ctx *ctx, int64_t G, const double *d_bb, const double *d_ms, double *d_out, double *d_coef);
 int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const double *d_mu0, const double *d_size0,
-                       double lower, double upper, const bn_fit_opts *opts, double *d_size_out, int32_t *d_conv,
-                       int32_t *d_nfe);
+                       double lower, double upper, const double *d_mm, const bn_fit_opts *opts, double *d_size_out,
+                       int32_t *d_conv, int32_t *d_nfe);
 
 extern "C" int bn_prior(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, int BB_SIZE, const bn_fit_opts *opts,
                         bn_prior_out *out)
@@ -37,21 +37,19 @@ extern "C" int bn_prior(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, int BB_S
     BN_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
     BN_TRY(bn_mme_device(ctx, m, beta.p, oMU.p, oSIZE.p, nullptr));
     BN_TRY(bn_size_bounds_device(ctx, m->G, oSIZE.p, stat.p));
-    double mm[2] = {0, 0};
+    // nothing below waits for the host: the box of the fit is read from device memory, so the whole
+    // prior (MME -> bounds -> fit -> adjust) is queued in one go and host scheduling noise (8 ranks,
+    // NCCL proxy threads) cannot open bubbles between the stages
+    double *mm = ctx->pinned, *coef_h = ctx->pinned + 2; // page-locked: the copies really are asynchronous
+    mm[0] = mm[1] = 0.0;
+    coef_h[0] = coef_h[1] = coef_h[2] = 0.0;
     BN_CUDA(ctx, cudaMemcpyAsync(mm, stat.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     BN_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
-    BN_TRY(bn_sync(ctx));
-    out->size_lower = mm[0];
-    out->size_upper = ceil(-mm[1]);
-    out->coef[0] = out->coef[1] = out->coef[2] = 0.0;
     if (BB_SIZE) {
-        if (!(mm[0] > 0.0) || !isfinite(mm[0]) || !isfinite(mm[1]))
-            return bn_fail(ctx, BN_ERR_INVALID, "no gene has a finite positive MME size (min %g, max %g)", mm[0], -mm[1]);
-        BN_TRY(bn_fit_size_device(ctx, m, beta.p, oMU.p, oSIZE.p, out->size_lower, out->size_upper, opts, oBB.p, oConv.p,
-                                  oNfe.p));
+        BN_TRY(bn_fit_size_device(ctx, m, beta.p, oMU.p, oSIZE.p, 0.0, 0.0, stat.p, opts, oBB.p, oConv.p, oNfe.p));
         BN_CUDA(ctx, cudaEventRecord(ev[2], ctx->stream));
         BN_TRY(bn_adjust_size_device(ctx, m->G, oBB.p, oSIZE.p, oADJ.p, stat.p + 2));
-        BN_CUDA(ctx, cudaMemcpyAsync(out->coef, stat.p + 2, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        BN_CUDA(ctx, cudaMemcpyAsync(coef_h, stat.p + 2, 24, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
         BN_CUDA(ctx, cudaEventRecord(ev[2], ctx->stream));
     }
@@ -63,6 +61,13 @@ extern "C" int bn_prior(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, int BB_S
     BN_TRY(oConv.commit(ctx));
     BN_TRY(oNfe.commit(ctx));
     BN_TRY(bn_sync(ctx));
+    out->size_lower = mm[0];
+    out->size_upper = ceil(-mm[1]);
+    out->coef[0] = coef_h[0];
+    out->coef[1] = coef_h[1];
+    out->coef[2] = coef_h[2];
+    if (BB_SIZE && (!(mm[0] > 0.0) || !isfinite(mm[0]) || !isfinite(mm[1])))
+        return bn_fail(ctx, BN_ERR_INVALID, "no gene has a finite positive MME size (min %g, max %g)", mm[0], -mm[1]);
     float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
     cudaEventElapsedTime(&t01, ev[0], ev[1]);
     cudaEventElapsedTime(&t12, ev[1], ev[2]);

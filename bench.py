@@ -53,6 +53,8 @@ CONFIGS = {
             G=33000, C=10000, m0=-0.675, out="sample", S=20, groups=1),
     7: dict(name="profiling proxy: sparse 33k x 20k (~8% nnz), GG, 2D mean",
             G=33000, C=20000, m0=-0.675, out="mean", S=1, groups=1),
+    8: dict(name="diagnostic: cfg2 x 8 gene blocks on one GPU (160k genes x 10k cells)",
+            G=160000, C=10000, m0=3.013, out="mode", S=1, groups=1),
     0: dict(name="tiny smoke configuration", G=1500, C=800, m0=-0.675, out="mode", S=1, groups=1),
 }
 # FP64 pipe instructions per likelihood term, counted in the SASS of k_fit_size:
