@@ -564,10 +564,11 @@ __global__ void __launch_bounds__(256, 3)
     __shared__ FitSlot slot[FIT_NS];
     __shared__ double scratch[FIT_NS][8];
     __shared__ double red8[8];
-    __shared__ int xmax_sh, n_running;
+    __shared__ int xmax_sh, n_running, queue_dry; // queue_dry: stop polling the global queue once it is empty
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bn_log_table_load(tab);
     if (tid < FIT_NS) slot[tid].state = 0;
+    if (tid == 0) queue_dry = 0;
     __syncthreads();
     for (;;) {
         // ---- refill idle slots (thread 0); all-zero genes are answered on the spot -------------
@@ -575,9 +576,12 @@ __global__ void __launch_bounds__(256, 3)
             int running = 0;
             for (int s = 0; s < FIT_NS; s++) {
                 FitSlot &sl = slot[s];
-                while (sl.state == 0) {
+                while (sl.state == 0 && !queue_dry) {
                     const unsigned long long gq = atomicAdd(queue, 1ULL);
-                    if (gq >= (unsigned long long)G) break;
+                    if (gq >= (unsigned long long)G) {
+                        queue_dry = 1;
+                        break;
+                    }
                     const int64_t gi = (int64_t)gq, a = rowptr[gi], n = rowptr[gi + 1] - a;
                     const double mu = mu0[gi];
                     if (n == 0 || !(mu > 0.0)) { // flat likelihood: spg returns the projected start

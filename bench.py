@@ -256,7 +256,7 @@ def run_ours(args):
         step()
     barrier_sync()
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BN_NO_CLOCKS"):
         clocks.start()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,11 +272,18 @@ def run_ours(args):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms_total = float(t.item())
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and not os.environ.get("BN_NO_CLOCKS")) else None
     ms_step = ms_total / args.steps
     value = elements_per_step * world / (ms_step * 1e-3)
     for k in phase:
         phase[k] /= args.steps
+    phase_all = None
+    if world > 1:          # per-rank phase times (the slowest rank sets the step)
+        keys = sorted(phase)
+        t = torch.tensor([phase[k] for k in keys], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        td.all_gather(gathered, t)
+        phase_all = {k: [float(g[i].item()) * 1e3 for g in gathered] for i, k in enumerate(keys)}
 
     # ---- fit statistics (solver-independent work measure) ---------------------------------------
     nfe = torch.stack([P["nfe"] for P in pri]).to(torch.float64)
@@ -334,7 +341,7 @@ def run_ours(args):
             "fit": {"genes_per_s": genes_per_step * world / fit_s, "ms": fit_s * 1e3,
                     "mean_evaluations_per_gene": evals / genes_per_step,
                     "likelihood_terms_per_s": (dense_terms + nz_terms) * world / fit_s},
-            "phases_ms": {k: v * 1e3 for k, v in phase.items()},
+            "phases_ms": {k: v * 1e3 for k, v in phase.items()}, "phases_ms_per_rank": phase_all,
             "roofline": dominant, "roofline_posterior": roof_post, "roofline_fit": roof_fit,
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "synth_seconds": gen_s,
         }
