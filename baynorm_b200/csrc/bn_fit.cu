@@ -20,6 +20,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "bn_internal.cuh"
 #include "bn_math.cuh"
 
@@ -540,6 +542,19 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
 // fold points and solver path do not depend on which genes share the CTA.
 // ---------------------------------------------------------------------------------
 #define FIT_NS 4
+#define FIT_EVCAP 128      // evaluations after which a gene is handed to the cluster kernel
+#define FIT_CL 8           // CTAs per cluster (portable maximum)
+#define FIT_CL_THREADS 512
+
+// A gene suspended by the sweep kernel: everything needed to resume its solver elsewhere.
+struct Straggler {
+    int64_t gene;
+    int nfe, kmax, n_big, pad;
+    double Kc, mu, next;
+    SpgState spg;
+    BrentState brent;
+    uint32_t tail[FitCfg<256>::HMAX + 1];
+};
 
 struct FitSlot {
     const uint64_t *nz;
@@ -556,7 +571,7 @@ __global__ void __launch_bounds__(256, 3)
                   const double *__restrict__ beta, const double *__restrict__ logbeta, const double *__restrict__ mu0,
                   const double *__restrict__ size0, const double *__restrict__ params, FitOpts o,
                   unsigned long long *__restrict__ queue, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
-                  int32_t *__restrict__ nfe_out)
+                  int32_t *__restrict__ nfe_out, Straggler *__restrict__ strag, unsigned int *__restrict__ n_strag)
 {
     const double lower = params[0], upper = params[1], beta_max = params[2]; // device-resident: no host round trip
     constexpr int HMAX = FitCfg<256>::HMAX;
@@ -749,9 +764,140 @@ __global__ void __launch_bounds__(256, 3)
                 if (conv_out) conv_out[sl.gene] = conv;
                 if (nfe_out) nfe_out[sl.gene] = sl.nfe;
                 sl.state = 0;
+            } else if (strag && sl.nfe >= FIT_EVCAP) {
+                // a straggler (BB::spg may run to maxit = 1500 iterations): one CTA would hold the tail of
+                // the whole launch for milliseconds, so park the solver state for the cluster kernel
+                Straggler &g = strag[atomicAdd(n_strag, 1u)];
+                g.gene = sl.gene;
+                g.nfe = sl.nfe;
+                g.kmax = sl.kmax;
+                g.n_big = sl.n_big;
+                g.Kc = sl.Kc;
+                g.mu = sl.mu;
+                g.next = sl.next;
+                g.spg = sl.spg;
+                g.brent = sl.brent;
+                for (int q = 0; q <= HMAX; q++) g.tail[q] = sl.tail[q];
+                sl.state = 0;
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Stragglers: one thread-block cluster (8 CTAs x 512 threads on neighbouring SMs) per gene.
+// Every evaluation is split over the 4096 threads of the cluster; the 8 CTA partial sums travel
+// to the leader CTA through distributed shared memory, the leader steps the solver and the next
+// trial size is read back by all CTAs the same way: two cluster barriers per evaluation instead
+// of a 256-thread CTA walking all cells alone.  Results stay deterministic (fixed cell -> thread
+// map and summation order; which genes are parked depends only on their own evaluation count).
+// ---------------------------------------------------------------------------------
+__global__ void __cluster_dims__(FIT_CL, 1, 1) __launch_bounds__(FIT_CL_THREADS, 1)
+    k_fit_cluster(int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
+                  const double *__restrict__ beta, FitOpts o, const Straggler *__restrict__ strag,
+                  const unsigned int *__restrict__ n_strag, double *__restrict__ size_out, int32_t *__restrict__ conv_out,
+                  int32_t *__restrict__ nfe_out)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int HMAX = FitCfg<256>::HMAX;
+    constexpr int NT = FIT_CL * FIT_CL_THREADS;
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    __shared__ Straggler st;             // leader's copy is the live solver state
+    __shared__ double part[FIT_CL];      // leader: partial sums of the 8 CTAs
+    __shared__ double warp_part[FIT_CL_THREADS / 32];
+    __shared__ double next_phi;          // leader: trial size of the coming evaluation (< 0: gene finished)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster.block_rank();
+    const int64_t t = (int64_t)rank * FIT_CL_THREADS + tid;
+    double *lead_part = cluster.map_shared_rank(part, 0);
+    const double *lead_next = cluster.map_shared_rank(&next_phi, 0);
+    bn_log_table_load(tab);
+    const unsigned n = *n_strag;
+    const unsigned ncluster = gridDim.x / FIT_CL;
+    for (unsigned w = blockIdx.x / FIT_CL; w < n; w += ncluster) {
+        // every CTA keeps a read-only copy of the gene's constants; the leader's copy also holds the solver
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(strag + w);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&st);
+            for (int q = tid; q < (int)(sizeof(Straggler) / 4); q += FIT_CL_THREADS) dst[q] = src[q];
+        }
+        __syncthreads();
+        if (rank == 0 && tid == 0) next_phi = st.next;
+        const int64_t a = rowptr[st.gene];
+        const uint64_t *__restrict__ nz = gm + a;
+        const int64_t nnz = rowptr[st.gene + 1] - a;
+        const double mu = st.mu;
+        cluster.sync();
+        for (;;) {
+            const double phi = *lead_next;
+            if (!(phi > 0.0)) break; // finished (sizes are positive: the box has lower > 0)
+            const double r = mu / phi;
+            double acc = 0.0, pa = 1.0, pb = 1.0;
+            if (fma(r, 1.0, 1.0) < 9.0e18) {
+                int64_t j = t;
+                for (; j + 15 * 2 * NT + NT < C; j += 16 * 2 * NT) {
+#pragma unroll 4
+                    for (int it = 0; it < 16; it++) {
+                        pa *= fma(r, __ldg(beta + j + it * 2 * NT), 1.0);
+                        pb *= fma(r, __ldg(beta + j + it * 2 * NT + NT), 1.0);
+                    }
+                    acc += bn_log(pa, tab) + bn_log(pb, tab);
+                    pa = 1.0;
+                    pb = 1.0;
+                }
+                for (; j < C; j += NT) pa *= fma(r, __ldg(beta + j), 1.0); // < 32 factors
+            } else {
+                for (int64_t j = t; j < C; j += NT) acc += bn_log(fma(r, __ldg(beta + j), 1.0), tab);
+            }
+            acc += bn_log(pa, tab) + bn_log(pb, tab);
+            double s0 = 0.0, s1 = 0.0;
+            for (int64_t k = t; k < nnz; k += NT) {
+                const uint64_t e0 = __ldg(nz + k);
+                const double x = (double)(uint32_t)e0;
+                s0 = fma(-x, bn_log(fma(mu, __ldg(beta + (e0 >> 32)), phi), tab), s0);
+                if (x > (double)HMAX) s1 += bn_lgamma_stirling(x + phi, tab) - bn_lgamma_stirling(phi + (double)HMAX, tab);
+            }
+            if (t < st.kmax) s1 = fma((double)st.tail[t], bn_log(phi + (double)t, tab), s1);
+            double tot = bn_warp_sum(-phi * acc + (s0 + s1));
+            if (lane == 0) warp_part[warp] = tot;
+            __syncthreads();
+            if (tid == 0) {
+                double c = 0.0;
+#pragma unroll
+                for (int q = 0; q < FIT_CL_THREADS / 32; q++) c += warp_part[q];
+                lead_part[rank] = c; // distributed shared memory store into the leader CTA
+            }
+            cluster.sync();
+            if (rank == 0 && tid == 0) {
+                double f = 0.0;
+#pragma unroll
+                for (int q = 0; q < FIT_CL; q++) f += part[q];
+                const double val = -(f + st.Kc);
+                st.nfe++;
+                bool more;
+                int conv;
+                if (o.method == BN_FIT_BRENT) {
+                    more = st.brent.step(val, o);
+                    st.next = st.brent.next;
+                    conv = st.brent.conv;
+                } else {
+                    more = st.spg.step(val, o);
+                    st.next = st.spg.next;
+                    conv = st.spg.conv;
+                }
+                if (!more) {
+                    size_out[st.gene] = st.next;
+                    if (conv_out) conv_out[st.gene] = conv;
+                    if (nfe_out) nfe_out[st.gene] = st.nfe;
+                    next_phi = -1.0;
+                } else
+                    next_phi = st.next;
+            }
+            cluster.sync();
+        }
+        cluster.sync(); // nobody may still be reading the leader's next_phi when the next gene is loaded
     }
 }
 
@@ -842,7 +988,19 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
         if (single < 0) single = getenv("BN_FIT_SINGLE_SLOT") ? 1 : 0; // A/B switch for profiling
         if (grad) BN_LAUNCH(ctx, (k_fit_size<256, true>), grid, 256, 0, FIT_ARGS);
         else if (single) BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
-        else BN_LAUNCH(ctx, k_fit_size_ms, (int)std::min<int64_t>((m->G + FIT_NS - 1) / FIT_NS, (int64_t)sms * 3), 256, 0, FIT_ARGS);
+        else {
+            // sweep kernel, then the cluster kernel for the genes it parked (usually none or a handful)
+            DevBuf<Straggler> strag;
+            DevBuf<unsigned int> nstrag;
+            BN_TRY(strag.alloc(ctx, (size_t)m->G));
+            BN_TRY(nstrag.alloc(ctx, 1));
+            BN_CUDA(ctx, cudaMemsetAsync(nstrag.p, 0, 4, ctx->stream));
+            BN_LAUNCH(ctx, k_fit_size_ms, (int)std::min<int64_t>((m->G + FIT_NS - 1) / FIT_NS, (int64_t)sms * 3), 256, 0,
+                      FIT_ARGS, strag.p, nstrag.p);
+            const int nclusters = std::max(1, sms / FIT_CL - 2);
+            BN_LAUNCH(ctx, k_fit_cluster, nclusters * FIT_CL, FIT_CL_THREADS, 0, m->C, m->rowptr, m->gm, d_beta, o, strag.p,
+                      nstrag.p, d_size_out, d_conv, d_nfe);
+        }
     } else {
         const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 24);
         if (grad) BN_LAUNCH(ctx, (k_fit_size<32, true>), grid, 128, 0, FIT_ARGS);

@@ -340,6 +340,8 @@ def run_ours(args):
                        "parallelism": "gene blocks x%d, all-reduce of per-cell totals + 3 small stats" % world},
             "fit": {"genes_per_s": genes_per_step * world / fit_s, "ms": fit_s * 1e3,
                     "mean_evaluations_per_gene": evals / genes_per_step,
+                    "max_evaluations_per_gene": float(nfe.max().item()),
+                    "genes_over_200_evaluations": int((nfe > 200).sum().item()),
                     "likelihood_terms_per_s": (dense_terms + nz_terms) * world / fit_s},
             "phases_ms": {k: v * 1e3 for k, v in phase.items()}, "phases_ms_per_rank": phase_all,
             "roofline": dominant, "roofline_posterior": roof_post, "roofline_fit": roof_fit,
