@@ -686,3 +686,38 @@ def test_mode_exact_fallback_near_integers(bn, ctx, oracle):
     got = bn.Main_mode_NB_Bay(bn.Check_input(X, ctx), beta, size, mu)
     assert np.array_equal(got, oracle.Main_mode_NB_Bay(Mo, beta, size, mu))
     assert np.array_equal(got, oracle.np_post_mode(X, beta, size, mu))
+
+
+def test_posterior_samples_every_path(bn, ctx, oracle):
+    """The three draw paths -- 32-point table (tiny means), warp-built 1024-point table (means in the tens)
+    and the gamma-Poisson fallback (means in the thousands) -- against the exact NB moments, on a matrix whose
+    non-zero fraction under-predicts the number of big-mean elements (forces the list-overflow repeat)."""
+    rng = np.random.default_rng(11)
+    G, C, S = 300, 120, 600
+    X = (rng.random((G, C)) < 0.03) * rng.integers(1, 4, (G, C)).astype(np.float64)
+    beta = rng.uniform(0.03, 0.2, C)
+    size = rng.uniform(0.5, 6.0, G)
+    mu = np.where(np.arange(G) % 3 == 0, 0.5, np.where(np.arange(G) % 3 == 1, 60.0, 4000.0)) * rng.uniform(0.5, 2.0, G)
+    Mo = oracle.CSC.from_dense(X)
+    M = bn.Check_input(X, ctx)
+    d = bn.Main_NB_Bay(M, beta, size, mu, S=S, seed=2024)
+    assert np.array_equal(d, np.floor(d)) and (d >= X[:, :, None]).all()
+    nb_size, nb_mu = oracle.post_sample_params(Mo, beta, size, mu)
+    mean_th = nb_mu + X
+    var_th = nb_mu + nb_mu ** 2 / nb_size
+    z = (d.mean(axis=2) - mean_th) / np.sqrt(var_th / S)
+    for cls in range(3):
+        zc = z[np.arange(G) % 3 == cls]
+        assert np.abs(zc).max() < 5.5 and abs(zc.mean()) < 4.5 / np.sqrt(zc.size), (cls, np.abs(zc).max(), zc.mean())
+    kap4 = var_th * (1 + 6 * var_th / nb_size)
+    vz = (d.var(axis=2, ddof=1) - var_th) / np.sqrt((kap4 + 2 * var_th ** 2) / S)
+    assert np.abs(vz).max() < 8
+    rng2 = np.random.default_rng(3)
+    from scipy.stats import chi2
+    for cls in range(3):
+        sel = np.arange(G) % 3 == cls
+        stat = _pooled_pit_chi2(d[sel], nb_size[sel], nb_mu[sel], X[sel], rng2)
+        assert stat < chi2.ppf(1 - 1e-6, 49), (cls, stat)
+    # purity across S and column blocks holds on every path
+    assert np.array_equal(bn.Main_NB_Bay(M, beta, size, mu, S=7, seed=2024), d[:, :, :7])
+    assert np.array_equal(bn.Main_NB_Bay(M, beta, size, mu, S=S, seed=2024, col0=17, ncol=40), d[:, 17:57, :])
