@@ -81,6 +81,7 @@ SIGNATURES = {
     "bn_debug_log": (C.c_int, [_VP, C.c_int, _VP, _I64, _VP]),
     "bn_mat_drop_gene_major": (C.c_int, [_VP]),
     "bn_debug_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "bn_debug_write_peak": (C.c_int, [_VP, _I64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -407,6 +407,42 @@ extern "C" int bn_debug_fp64_peak(bn_ctx *ctx, double *flops_per_s)
     return BN_OK;
 }
 
+// Measured HBM WRITE bandwidth (GB/s): the posterior kernels are write-only streams, so this -- not the
+// read+write copy figure -- is what they can reach.  pattern 0: one linear stream, every warp store
+// 256 contiguous bytes; pattern 1: the 3-D layout, a warp stores 256 B to each of `planes` planes
+// (bytes/planes apart), `run` stores of 256 B per visit, before moving on, like the S draws of one gene block.
+__global__ void __launch_bounds__(256) k_write_peak(double *out, int64_t n, int planes, int run)
+{
+    const int64_t per_plane = n / planes;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t step = 32 * (int64_t)run; // elements a warp writes to one plane before switching
+    for (int64_t c = warp * step; c + step <= per_plane; c += nwarps * step)
+        for (int s = 0; s < planes; s++)
+            for (int q = 0; q < run; q++) __stcs(out + s * per_plane + c + q * 32 + lane, (double)(c + s));
+}
+
+extern "C" int bn_debug_write_peak(bn_ctx *ctx, int64_t bytes, int planes, int run, double *gb_per_s)
+{
+    if (!ctx || !gb_per_s || bytes < (1 << 20) || planes < 1 || run < 1) return BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const int64_t n = bytes / 8;
+    DevBuf<double> o;
+    BN_TRY(o.alloc(ctx, (size_t)n));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        BN_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+        BN_LAUNCH(ctx, k_write_peak, ctx->prop.multiProcessorCount * 16, 256, 0, o.p, n, planes, run);
+        BN_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        BN_TRY(bn_sync(ctx));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *gb_per_s = (double)(n / planes / (32 * run) * (32 * run) * planes) * 8.0 / (best * 1e-3) / 1e9;
+    return BN_OK;
+}
+
 extern "C" int bn_mat_set_origin(bn_mat *m, int64_t gene0, int64_t cell0)
 {
     if (!m || gene0 < 0 || cell0 < 0) return BN_ERR_INVALID;

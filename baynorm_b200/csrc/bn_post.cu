@@ -210,6 +210,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // A Philox word at or beyond the last tabulated threshold: continue the pmf recurrence from k = SAMPLE_K - 1
 // until the (2^32-scaled) CDF passes it.  The walk ends as well once p(k) no longer moves the float CDF: the
@@ -241,20 +248,24 @@ struct HeavyItem {
 // strip, own table columns, own block of the heavy list.  There is no __syncthreads() in the loop:
 // a warp delayed by a tail walk never holds up the other seven.
 #define SW_GENES 128
-#define SW_WARPS 8
-#define SW_TG (SW_GENES * SW_WARPS)
 #define SW_HBLOCK 64 // heavy-list slots a warp reserves per global atomic
+#define SW_PLANES 32 // planes staged per pass (one byte per draw)
+#define SW_SMEM_PER_WARP (SAMPLE_K * 32 * 4 + SW_GENES * 8 + SW_PLANES * SW_GENES)
 
-__global__ void __launch_bounds__(SW_WARPS * 32, 4)
+template <int SW_WARPS, int MINB>
+__global__ void __launch_bounds__(SW_WARPS * 32, MINB)
     k_post_sample(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                   const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
                   const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
                   int S, const __grid_constant__ PhiloxKeys keys, int64_t gene0, int64_t cell0, int64_t sstride,
                   HeavyItem *__restrict__ hlist, unsigned int *__restrict__ hcount, unsigned int hcap)
 {
-    __shared__ uint32_t s_tab[SW_WARPS][SAMPLE_K * 32]; // [warp][k][lane]: one conflict-free column per thread
-    __shared__ double s_x[SW_WARPS][SW_GENES];          // the warp's counts of the current column (0 = absent)
+    constexpr int SW_TG = SW_GENES * SW_WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xt = reinterpret_cast<double *>(smem_raw) + warp * SW_GENES;                                  // the warp's counts of the current column (0 = absent)
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw + SW_WARPS * SW_GENES * 8) + warp * SAMPLE_K * 32; // [k][lane]: one conflict-free column per thread
+    unsigned char *s_stage = smem_raw + SW_WARPS * (SW_GENES * 8 + SAMPLE_K * 32 * 4) + warp * (SW_PLANES * SW_GENES); // [plane][gene]: draws of the current column
     const int64_t w0 = (int64_t)blockIdx.x * SW_TG + (int64_t)warp * SW_GENES; // first gene of this warp
     const int64_t wend = w0 + SW_GENES;
     const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
@@ -262,15 +273,18 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
     if (w0 >= G) return;
     // slice starts of columns lane and lane + 32 of the chunk (a shard holds < 2^32 non-zeros)
     uint32_t lo_a = 0, end_a = 0, lo_b = 0, end_b = 0;
+    float beta_a = 0.0f, beta_b = 0.0f; // BETA of the same two columns
     if (lane < nc) {
         const int64_t j = col0 + jb + lane;
         const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
+        beta_a = (float)__ldg(beta + j);
         end_a = (uint32_t)ce;
         lo_a = (uint32_t)((w0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, w0));
     }
     if (lane + 32 < nc) {
         const int64_t j = col0 + jb + lane + 32;
         const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
+        beta_b = (float)__ldg(beta + j);
         end_b = (uint32_t)ce;
         lo_b = (uint32_t)((w0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, w0));
     }
@@ -278,7 +292,6 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
     // tempmu = (x + size)(mu - mu beta)/(size + mu beta) (:1118) are evaluated in float too: a relative 1e-7 in a
     // parameter is far below what any test of the draws can resolve, and it frees 8 registers and an FP64 division.
     float sz[4], m[4];
-    double *xt = s_x[warp];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         const int64_t i = w0 + e * 32 + lane;
@@ -287,7 +300,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
         xt[e * 32 + lane] = 0.0;
     }
     // this thread's column of the threshold table, as a 32-bit shared-memory address: entry k at tsa + SOFF(k)
-    const uint32_t tsa = (uint32_t)__cvta_generic_to_shared(&s_tab[warp][lane]);
+    const uint32_t tsa = (uint32_t)__cvta_generic_to_shared(s_tab + lane);
+    const uint32_t ssa = (uint32_t)__cvta_generic_to_shared(s_stage + lane); // draw (plane s, element e) at ssa + s * SW_GENES + e * 32
 #define SOFF(k) ((k) * 32 * 4)
     unsigned hblock = 0, hused = SW_HBLOCK; // heavy-list block of this warp (warp-uniform)
     // slice of column 0 into registers
@@ -331,13 +345,18 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
             }
         }
         const int64_t jl = jb + jj, j = col0 + jl;
-        const float bf = (float)__ldg(beta + j);
+        const float bf = __shfl_sync(0xffffffffu, (jj < 32) ? beta_a : beta_b, jj & 31);
+        // The S draws of the column go through a byte-per-draw staging strip and leave as 1 KB runs per plane
+        // (4 x 256 B, the warp's 128 genes): the dim = c(G, C, S) layout puts the planes G*ncol apart, and HBM
+        // sustains 5.5 TB/s with 1 KB per plane visit against 4.0 TB/s with 256 B (bn_debug_write_peak).
+        // 255 in the strip = not written here (big-mean element: other kernels; draw >= 255: stored directly).
+        for (int sb = 0; sb < S; sb += SW_PLANES) { // one pass unless S > SW_PLANES
+        const int nS = min(S - sb, SW_PLANES);
 #pragma unroll 1
         for (int e = 0; e < 4; e++) {
             const int64_t i = w0 + e * 32 + lane;
             const bool in = i < G;
             const double xv = xt[e * 32 + lane];
-            xt[e * 32 + lane] = 0.0; // own slot: ready for the next column's scatter
             // size/mu of the current gene sit in sz[0], m[0]; the arrays are rotated at the end of the step so
             // that they stay in registers (a dynamic index would put them in local memory)
             const float mbf = m[0] * bf;
@@ -348,7 +367,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
                 sz[0] = sz[1], sz[1] = sz[2], sz[2] = sz[3], sz[3] = s_;
                 m[0] = m[1], m[1] = m[2], m[2] = m[3], m[3] = m_;
             }
-            double *o = out + G * jl + i;
+            double *o = out + G * jl + i + sstride * sb;
             // first SAMPLE_K points of the CDF, scaled by 2^32:  p(0) = (r/(r+M))^r,
             // p(k) = p(k-1) * q (r + k - 1)/k = p(k-1) * (q + q (r - 1)/k),  q = M/(r+M)
             const float q = __fdividef(Mf, rf + Mf), c1 = q * (rf - 1.0f);
@@ -369,7 +388,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
             // append the heavy elements of this step to the warp's block of the global list; a new block
             // (one global atomic per SW_HBLOCK slots) is reserved when the current one cannot take them,
             // the slots left over are marked empty
-            const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+            const unsigned hm = (sb == 0) ? __ballot_sync(0xffffffffu, heavy) : 0u;
             if (hm) {
                 const unsigned n = (unsigned)__popc(hm);
                 if (hused + n > SW_HBLOCK) {
@@ -394,10 +413,13 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
                 }
                 hused += n;
             }
-            if (in && !pos) { // rgamma(shape, scale = 0) = 0 -> rpois(0) = 0: the draw is x itself
-                for (int s = 0; s < S; s++) __stcs(o + sstride * s, xv);
-            }
-            if (light) {
+            uint32_t sp = ssa + e * 32; // staging slot of (plane sb, this element)
+            if (!light) {
+                // mean 0 (rgamma(shape, scale = 0) = 0 -> rpois(0) = 0): the draw is x itself, staged as k = 0;
+                // big-mean and out-of-range elements: 255 = not written by this kernel
+                const uint32_t fill = (in && !pos) ? 0u : 255u;
+                for (int s = 0; s < nS; s++) sts_u8(sp + s * SW_GENES, fill);
+            } else {
                 const uint32_t c0 = (uint32_t)(gene0 + i), c1p = (uint32_t)(cell0 + j);
                 const uint32_t t31 = lds_u32(tsa + SOFF(SAMPLE_K - 1));
                 double *po = o;
@@ -407,13 +429,14 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
                  "@p add.u32 %0, %0, %3;\n\t}"                                                                         \
                  : "+r"(A)                                                                                             \
                  : "r"(U), "n"(SOFF(PROBE)), "n"(SOFF(STEP)))
-#define SVALUE(A) fma((double)(A - tsa), 1.0 / (double)SOFF(1), xv)
-#define SDRAW(A, U)                                                                                              \
+#define SKVAL(A) ((A - tsa) / SOFF(1))
+                // slow path of one draw: beyond the table (~0.1 % of draws), or a draw that does not fit a byte
+#define SDRAW(A, U, PLANE)                                                                                       \
     do {                                                                                                         \
-        double v_ = SVALUE(A);                                                                                   \
-        if (U >= t31) { /* beyond the table: ~0.1 % of draws */                                                  \
+        uint32_t k_ = SKVAL(A);                                                                                  \
+        if (U >= t31) {                                                                                          \
             const float kk_ = sample_tail(U, p, ctop, c1, q);                                                    \
-            if (kk_ >= 0.0f) v_ = (double)kk_ + xv;                                                              \
+            if (kk_ >= 0.0f) k_ = (uint32_t)kk_;                                                                 \
             else { /* rounding deficit of a complete table: the last point that still carries mass */            \
                 uint32_t a_ = tsa;                                                                               \
                 const uint32_t u_ = t31 - 1u;                                                                    \
@@ -422,16 +445,19 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
                 SLEVEL(a_, u_, 3, 4);                                                                            \
                 SLEVEL(a_, u_, 1, 2);                                                                            \
                 SLEVEL(a_, u_, 0, 1);                                                                            \
-                v_ = SVALUE(a_);                                                                                 \
+                k_ = SKVAL(a_);                                                                                  \
             }                                                                                                    \
         }                                                                                                        \
-        __stcs(po, v_);                                                                                          \
-        po += sstride;                                                                                           \
+        if (k_ >= 255u) {                                                                                        \
+            __stcs(po + sstride * (PLANE), (double)k_ + xv);                                                     \
+            k_ = 255u;                                                                                           \
+        }                                                                                                        \
+        sts_u8(sp + (PLANE) * SW_GENES, k_);                                                                     \
     } while (0)
                 int s0 = 0;
-                for (; s0 + 4 <= S; s0 += 4) {
+                for (; s0 + 4 <= nS; s0 += 4) {
                     uint32_t u0, u1, u2, u3;
-                    bn_philox_block(keys, c0, c1p, (uint32_t)(s0 >> 2), 0u, u0, u1, u2, u3);
+                    bn_philox_block(keys, c0, c1p, (uint32_t)((sb + s0) >> 2), 0u, u0, u1, u2, u3);
                     uint32_t a0 = tsa, a1 = tsa, a2 = tsa, a3 = tsa;
                     SLEVEL(a0, u0, 15, 16); SLEVEL(a1, u1, 15, 16); SLEVEL(a2, u2, 15, 16); SLEVEL(a3, u3, 15, 16);
                     SLEVEL(a0, u0, 7, 8);   SLEVEL(a1, u1, 7, 8);   SLEVEL(a2, u2, 7, 8);   SLEVEL(a3, u3, 7, 8);
@@ -439,41 +465,68 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4)
                     SLEVEL(a0, u0, 1, 2);   SLEVEL(a1, u1, 1, 2);   SLEVEL(a2, u2, 1, 2);   SLEVEL(a3, u3, 1, 2);
                     SLEVEL(a0, u0, 0, 1);   SLEVEL(a1, u1, 0, 1);   SLEVEL(a2, u2, 0, 1);   SLEVEL(a3, u3, 0, 1);
                     const uint32_t umax = max(max(u0, u1), max(u2, u3));
-                    if (umax < t31) { // all four inside the table (the common case): straight-line stores
-                        __stcs(po, SVALUE(a0));
-                        __stcs(po + sstride, SVALUE(a1));
-                        __stcs(po + 2 * sstride, SVALUE(a2));
-                        __stcs(po + 3 * sstride, SVALUE(a3));
-                        po += 4 * sstride;
+                    if (umax < t31) { // all four inside the table (the common case; k < 32 fits the byte)
+                        sts_u8(sp, SKVAL(a0));
+                        sts_u8(sp + SW_GENES, SKVAL(a1));
+                        sts_u8(sp + 2 * SW_GENES, SKVAL(a2));
+                        sts_u8(sp + 3 * SW_GENES, SKVAL(a3));
                     } else {
-                        SDRAW(a0, u0);
-                        SDRAW(a1, u1);
-                        SDRAW(a2, u2);
-                        SDRAW(a3, u3);
+                        SDRAW(a0, u0, 0);
+                        SDRAW(a1, u1, 1);
+                        SDRAW(a2, u2, 2);
+                        SDRAW(a3, u3, 3);
                     }
+                    sp += 4 * SW_GENES;
+                    po += 4 * sstride;
                 }
-                if (s0 < S) { // S is not a multiple of 4: the last, partial Philox block
+                if (s0 < nS) { // S is not a multiple of 4: the last, partial Philox block
                     uint32_t u[4];
-                    bn_philox_block(keys, c0, c1p, (uint32_t)(s0 >> 2), 0u, u[0], u[1], u[2], u[3]);
+                    bn_philox_block(keys, c0, c1p, (uint32_t)((sb + s0) >> 2), 0u, u[0], u[1], u[2], u[3]);
 #pragma unroll
                     for (int w = 0; w < 3; w++) {
-                        if (s0 + w < S) {
+                        if (s0 + w < nS) {
                             uint32_t a0 = tsa;
                             SLEVEL(a0, u[w], 15, 16);
                             SLEVEL(a0, u[w], 7, 8);
                             SLEVEL(a0, u[w], 3, 4);
                             SLEVEL(a0, u[w], 1, 2);
                             SLEVEL(a0, u[w], 0, 1);
-                            SDRAW(a0, u[w]);
+                            SDRAW(a0, u[w], w);
                         }
                     }
                 }
 #undef SDRAW
-#undef SVALUE
+#undef SKVAL
 #undef SLEVEL
             }
             __syncwarp(); // reconverge before the next element's table is written
         }
+        // flush: plane by plane, the warp's 128 genes as four back-to-back 256 B stores
+        {
+            double xe[4];
+            bool ine[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                xe[e] = xt[e * 32 + lane];
+                ine[e] = w0 + e * 32 + lane < G;
+            }
+            double *po = out + G * jl + w0 + lane + sstride * sb;
+            uint32_t sp = ssa;
+            for (int s = 0; s < nS; s++) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t kb = lds_u8(sp + e * 32);
+                    if (kb != 255u && ine[e]) __stcs(po + e * 32, xe[e] + (double)kb);
+                }
+                sp += SW_GENES;
+                po += sstride;
+            }
+        }
+        __syncwarp(); // the strip is rewritten by the next pass / column
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) xt[e * 32 + lane] = 0.0; // own slots: ready for the next column's scatter
+        __syncwarp();
     }
     // close the warp's last heavy-list block
     if (hused < SW_HBLOCK && hblock + SW_HBLOCK <= hcap) {
@@ -674,6 +727,8 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
     DevOut<double> o;
     BN_TRY(o.bind(ctx, out, nout));
     if (mode == POST_SAMPLE) {
+        constexpr int SW_WARPS = 8; // 8 warps x 9 KB of shared memory: 3 CTAs per SM
+        const int64_t SW_TG = (int64_t)SW_GENES * SW_WARPS;
         const int64_t tiles_s = (m->G + SW_TG - 1) / SW_TG;
         const int sms = ctx->prop.multiProcessorCount;
         // Capacity of the list of elements the 32-point table cannot cover.  Worst case: every element, plus the
@@ -685,8 +740,10 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         for (int attempt = 0; attempt < 2; attempt++) {
             const double per_elem = attempt == 0 ? std::min(2.0, std::max(0.125, 6.0 * rho)) : 2.0;
             const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, (int64_t)(((int64_t)1 << 30) / (sizeof(HeavyItem) * per_elem * (double)m->G))));
-            // CTAs of any chunk: <= tiles * ceil(chunk / 64) when 64 columns per CTA already fill the GPU, else < 2 * 16 per SM
-            const size_t max_ctas = (size_t)std::max<int64_t>(tiles_s * ((chunk + POST_NCMAX - 1) / POST_NCMAX), (int64_t)sms * 32) + (size_t)tiles_s;
+            // CTAs of any chunk: tiles * ceil(chunk / 64) when 64 columns per CTA already give 64 CTAs per SM; otherwise
+            // the halving stops below 2 * 64 per SM (+ one row of tiles) or at 4 columns per CTA
+            const int64_t ctas64 = tiles_s * ((chunk + POST_NCMAX - 1) / POST_NCMAX), ctas4 = tiles_s * ((chunk + 3) / 4);
+            const size_t max_ctas = (size_t)std::max<int64_t>(ctas64, std::min<int64_t>(ctas4, (int64_t)sms * 128 + tiles_s));
             const size_t cap = (((size_t)(per_elem * (double)m->G * (double)chunk) + SW_HBLOCK - 1) / SW_HBLOCK + (size_t)SW_WARPS * max_ctas) * SW_HBLOCK; // whole blocks
             if (cap > 0xfffffff0u) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: element list too long");
             DevBuf<HeavyItem> hl, fl;
@@ -697,16 +754,21 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
             BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 4 * sizeof(unsigned int), ctx->stream));
             for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
                 const int64_t nc_ = std::min<int64_t>(chunk, ncol - c0);
-                int ncs = POST_NCMAX; // columns per CTA: >= 16 CTAs per SM so that the last wave is short
-                while (ncs > 1 && tiles_s * ((nc_ + ncs - 1) / ncs) < (int64_t)sms * 16) ncs >>= 1;
+                int ncs = POST_NCMAX; // columns per CTA: short walks keep the columns in flight (and their 20 planes) close together
+                while (ncs > 4 && tiles_s * ((nc_ + ncs - 1) / ncs) < (int64_t)sms * 64) ncs >>= 1;
+                if (const char *e = getenv("BN_SAMPLE_NCS")) ncs = std::max(1, std::min(POST_NCMAX, atoi(e)));
                 if ((nc_ + ncs - 1) / ncs > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
                 dim3 grid_s((unsigned)tiles_s, (unsigned)((nc_ + ncs - 1) / ncs));
                 BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 2 * sizeof(unsigned int), ctx->stream));
                 BN_CUDA(ctx, cudaMemsetAsync(hc.p + 3, 0, sizeof(unsigned int), ctx->stream));
                 // out is addressed relative to the chunk's first column; planes stay G*ncol apart
-                BN_LAUNCH(ctx, k_post_sample, grid_s, SW_WARPS * 32, 0, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p,
-                          col0 + c0, nc_, ncs, o.p + m->G * c0, S, bn_philox_keys(seed), m->gene0, m->cell0, m->G * ncol, hl.p, hc.p,
-                          (unsigned)cap);
+#define SAMPLE_ARGS                                                                                                    \
+    m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p, col0 + c0, nc_, ncs, o.p + m->G * c0, S, bn_philox_keys(seed), m->gene0, \
+        m->cell0, m->G * ncol, hl.p, hc.p, (unsigned)cap
+                const size_t smem_s = (size_t)SW_WARPS * SW_SMEM_PER_WARP;
+                BN_CUDA(ctx, cudaFuncSetAttribute(k_post_sample<SW_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                BN_LAUNCH(ctx, (k_post_sample<SW_WARPS, 3>), grid_s, SW_WARPS * 32, smem_s, SAMPLE_ARGS);
+#undef SAMPLE_ARGS
                 BN_LAUNCH(ctx, k_post_sample_table, sms * 4, HT_WARPS * 32, 0, m->G, hl.p, hc.p, S, bn_philox_keys(seed), m->gene0, m->cell0,
                           col0 + c0, m->G * ncol, o.p + m->G * c0, fl.p, hc.p + 1, (unsigned)cap, hc.p + 3);
                 BN_LAUNCH(ctx, k_post_sample_heavy, sms * 8, 256, 0, m->G, fl.p, hc.p + 1, S, seed, m->gene0, m->cell0, col0 + c0, m->G * ncol,

@@ -457,6 +457,15 @@ def cpu_reference(args, cfg, G, C, S, out_kind, csc, genes_sample, cols_sample, 
             "mean_evals_per_gene": float((cnt[:, 0] + cnt[:, 1]).mean())}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -474,6 +483,12 @@ def main():
     ap.add_argument("--cpu-genes", type=int, default=0, help="genes in the CPU fit sample (0 = auto)")
     ap.add_argument("--cpu-cols", type=int, default=0, help="columns in the CPU posterior sample (0 = auto)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that print to fd 1 (NCCL's version banner under
+    # torchrun) are sent to stderr for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours" and args.config != 0:
         args.warmup = 3                     # timing rule: W >= 3
     rank = int(os.environ.get("RANK", "0"))
@@ -489,7 +504,7 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             result["cpu_baseline"] = cpu_baseline_block(args, cfg, M, G, C, S, out_kind)
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         import torch.distributed as td
         td.barrier()
@@ -576,7 +591,7 @@ def main_reference(args, cfg):
                              "sample": sample, "detail": detail},
             "e2e": {"value": value, "unit": "posterior elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

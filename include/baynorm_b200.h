@@ -216,6 +216,10 @@ BN_API int bn_downsample(bn_ctx *ctx, int64_t G, int64_t C, const double *Data, 
 BN_API int bn_mat_drop_gene_major(bn_mat *m);
 /* Measured FP64 FMA rate of the device in flop/s (roofline denominator of the fit kernel). */
 BN_API int bn_debug_fp64_peak(bn_ctx *ctx, double *flops_per_s);
+/* Measured HBM write-only bandwidth in GB/s over a `bytes`-sized buffer, written as one stream
+ * (planes = 1) or in the dim = c(G, C, S) pattern of the 3-D output (planes = S; a warp writes
+ * run x 256 contiguous bytes to a plane before it moves to the next). */
+BN_API int bn_debug_write_peak(bn_ctx *ctx, int64_t bytes, int planes, int run, double *gb_per_s);
 
 /* ---- debug ------------------------------------------------------------------------- */
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
