@@ -173,19 +173,51 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
         if (mode == 2) {
             mean = means_in[g];
         } else {
-            double s = 0.0;
-            for (int64_t k = a + lane; k < b; k += 32) {
+            // four independent loads / divisions / partial sums per lane: the loop is latency-bound otherwise
+            double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int64_t k = a + lane;
+            for (; k + 96 < b; k += 128) {
+                double x0, x1, x2, x3;
+                int c0, c1, c2, c3;
+                nz_load<PACKED>(gm, cell, rval, k, c0, x0);
+                nz_load<PACKED>(gm, cell, rval, k + 32, c1, x1);
+                nz_load<PACKED>(gm, cell, rval, k + 64, c2, x2);
+                nz_load<PACKED>(gm, cell, rval, k + 96, c3, x3);
+                if (beta) {
+                    const double b0 = __ldg(beta + c0), b1 = __ldg(beta + c1), b2 = __ldg(beta + c2), b3 = __ldg(beta + c3);
+                    x0 = __ddiv_rn(x0, b0), x1 = __ddiv_rn(x1, b1), x2 = __ddiv_rn(x2, b2), x3 = __ddiv_rn(x3, b3);
+                }
+                s += x0, s1 += x1, s2 += x2, s3 += x3;
+            }
+            for (; k < b; k += 32) {
                 double x;
                 int c;
                 nz_load<PACKED>(gm, cell, rval, k, c, x);
                 s += beta ? __ddiv_rn(x, __ldg(beta + c)) : x;
             }
+            s = (s + s1) + (s2 + s3);
             mean = __ddiv_rn(bn_warp_sum(s), n); // :1316-1318
             if (lane == 0 && MU) MU[g] = mean;
             if (mode == 1) continue;
         }
-        double ss = 0.0;
-        for (int64_t k = a + lane; k < b; k += 32) {
+        double ss = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
+        int64_t k = a + lane;
+        for (; k + 96 < b; k += 128) {
+            double x0, x1, x2, x3;
+            int c0, c1, c2, c3;
+            nz_load<PACKED>(gm, cell, rval, k, c0, x0);
+            nz_load<PACKED>(gm, cell, rval, k + 32, c1, x1);
+            nz_load<PACKED>(gm, cell, rval, k + 64, c2, x2);
+            nz_load<PACKED>(gm, cell, rval, k + 96, c3, x3);
+            if (beta) {
+                const double b0 = __ldg(beta + c0), b1 = __ldg(beta + c1), b2 = __ldg(beta + c2), b3 = __ldg(beta + c3);
+                x0 = __ddiv_rn(x0, b0), x1 = __ddiv_rn(x1, b1), x2 = __ddiv_rn(x2, b2), x3 = __ddiv_rn(x3, b3);
+            }
+            const double d0 = __dsub_rn(x0, mean), d1 = __dsub_rn(x1, mean), d2 = __dsub_rn(x2, mean), d3 = __dsub_rn(x3, mean);
+            ss = __dadd_rn(ss, __dmul_rn(d0, d0)), ss1 = __dadd_rn(ss1, __dmul_rn(d1, d1));
+            ss2 = __dadd_rn(ss2, __dmul_rn(d2, d2)), ss3 = __dadd_rn(ss3, __dmul_rn(d3, d3));
+        }
+        for (; k < b; k += 32) {
             double x;
             int c;
             nz_load<PACKED>(gm, cell, rval, k, c, x);
@@ -193,7 +225,7 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
             const double d = __dsub_rn(v, mean);
             ss = __dadd_rn(ss, __dmul_rn(d, d)); // :1331
         }
-        ss = bn_warp_sum(ss);
+        ss = bn_warp_sum((ss + ss1) + (ss2 + ss3));
         if (lane == 0) {
             const double nz = (double)(b - a);
             double var = __dadd_rn(ss, __dmul_rn(__dsub_rn(n, nz), __dmul_rn(mean, mean))); // :1338
