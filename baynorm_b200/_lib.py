@@ -80,6 +80,8 @@ SIGNATURES = {
     "bn_debug_philox": (C.c_int, [_VP, _VP, _VP, _VP]),
     "bn_debug_log": (C.c_int, [_VP, C.c_int, _VP, _I64, _VP]),
     "bn_mat_drop_gene_major": (C.c_int, [_VP]),
+    "bn_synthetic_control": (C.c_int, [_VP, _VP, _VP, _U64, _VP, _VP]),
+    "bn_beta_fun": (C.c_int, [_VP, _VP, _D, _VP, _VP, _VP]),
     "bn_debug_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "bn_debug_write_peak": (C.c_int, [_VP, _I64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }

@@ -388,6 +388,41 @@ def DownSampling(Data, BETA_vec, seed=None, ctx=None):
     return out
 
 
+def BetaFun(Data, MeanBETA, ctx=None, rownames=None, with_stats=False):
+    """R/PRIOR_FUNCTIONS.R:30-71: capture efficiencies from the library sizes of the genes whose largest
+    log(normalised count + 1) is below median + 3 MAD and that are zero in fewer than 35 % of the cells.
+    Returns {"BETA", "Selected_genes"} like the reference's list (gene names if `rownames` is given or Data
+    carries them, else 0-based row indices); with_stats adds the per-gene median / mad / max / zero fraction."""
+    ctx = ctx or default_context()
+    M = Data if isinstance(Data, DeviceMatrix) else Check_input(Data, ctx, rownames=rownames)
+    beta = np.empty(M.C, dtype=_F64)
+    sel = np.empty(M.G, dtype=np.int32)
+    stats = np.empty(4 * M.G, dtype=_F64)
+    ctx.check(ctx.lib.bn_beta_fun(ctx.h, M.h, float(MeanBETA), _ptr(beta), _ptr(sel), _ptr(stats)))
+    idx = np.nonzero(sel)[0]
+    names = rownames if rownames is not None else getattr(M, "rownames", None)
+    out = {"BETA": beta, "Selected_genes": [names[i] for i in idx] if names is not None else idx}
+    if with_stats:
+        st = stats.reshape(4, M.G)
+        out["stats"] = {"median": st[0], "mad": st[1], "max": st[2], "dropout": st[3]}
+    return out
+
+
+def SyntheticControl(Data, BETA_vec, seed=None, ctx=None):
+    """R/synthetic_controls.r:57-70: Poisson control counts with the genes' normalised means, binomially
+    down-sampled with the cells' capture efficiencies.  Returns {"N_c", "beta_c", "lambda"} like the
+    reference's list; the G x C Poisson matrix is never materialised (one fused kernel)."""
+    ctx = ctx or default_context()
+    M = Data if isinstance(Data, DeviceMatrix) else Check_input(Data, ctx)
+    b = _vec(BETA_vec, M.C, "BETA_vec")
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
+    lam = np.empty(M.G, dtype=_F64)
+    N_c = np.empty((M.G, M.C), dtype=_F64, order="F")
+    ctx.check(ctx.lib.bn_synthetic_control(ctx.h, M.h, _ptr(b), int(seed) & (2 ** 64 - 1), _ptr(lam), _ptr(N_c)))
+    return {"N_c": N_c, "beta_c": b, "lambda": lam}
+
+
 # --------------------------------------------------------------------------------------
 # R-level functions
 # --------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "bn_internal.cuh"
+#include "bn_rng.cuh"
 
 // ---------------------------------------------------------------------------------
 // column sums: one warp per cell column, 8 columns per 256-thread CTA
@@ -318,6 +319,86 @@ extern "C" int bn_mme_dense(bn_ctx *ctx, int64_t G, int64_t C, const double *den
     int rc = bn_mme_impl(ctx, m, 3, nullptr, MU, SIZE, V);
     bn_mat_free(m);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// SyntheticControl (R/synthetic_controls.r:57-70): lambda_i = rowMeans(t(t(Data)/colSums(Data)) * Mean_depth)
+// with Mean_depth = mean(colSums(Data)/BETA), then N_c[i,j] = DownSampling(rpois(lambda_i), BETA_j)
+// = rbinom(1, rpois(1, lambda_i), BETA_j).  The column sums, the per-gene means and the draws are three
+// streaming passes; the G x C Poisson matrix of the reference is never materialised.
+// ---------------------------------------------------------------------------------
+// depth[0] = mean_j xx_j / beta_j ; status[0] |= 1 when a cell has no counts (the reference then propagates NaN)
+__global__ void __launch_bounds__(1024) k_mean_depth(int64_t C, const double *__restrict__ xx, const double *__restrict__ beta,
+                                                     double *__restrict__ depth, int *__restrict__ status)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    int bad = 0;
+    for (int64_t j = threadIdx.x; j < C; j += blockDim.x) {
+        s += __ddiv_rn(xx[j], beta[j]);
+        bad |= !(xx[j] > 0.0);
+    }
+    const double tot = block_reduce_1024<RED_SUM>(s, sh);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        depth[0] = __ddiv_rn(tot, (double)C);
+        status[0] = bad;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scale_vec(int64_t n, double *__restrict__ v, const double *__restrict__ factor)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) v[k] = __dmul_rn(v[k], factor[0]);
+}
+
+__global__ void __launch_bounds__(256) k_synthetic_control(int64_t G, int64_t C, const double *__restrict__ lambda,
+                                                           const double *__restrict__ beta, uint64_t seed, int64_t gene0,
+                                                           int64_t cell0, double *__restrict__ out)
+{
+    const int64_t total = G * C;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += gridDim.x * (int64_t)blockDim.x) {
+        const int64_t j = e / G, i = e - j * G;
+        Philox g;
+        g.init(seed, (uint64_t)(gene0 + i) + (uint64_t)(cell0 + j) * 0x100000000ULL, 0x53433031u /* "SC01" */);
+        const double n = bn_rpois(g, __ldg(lambda + i));
+        __stcs(out + e, n > 0.0 ? bn_rbinom(g, n, __ldg(beta + j)) : 0.0);
+    }
+}
+
+extern "C" int bn_synthetic_control(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, uint64_t seed, double *lambda,
+                                    double *N_c)
+{
+    if (!ctx || !m || !BETA_vec) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_synthetic_control: NULL argument") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> b;
+    BN_TRY(b.bind(ctx, BETA_vec, (size_t)m->C));
+    DevOut<double> olam, onc;
+    BN_TRY(olam.bind(ctx, lambda, (size_t)m->G, true));
+    BN_TRY(onc.bind(ctx, N_c, (size_t)m->G * (size_t)m->C));
+    DevBuf<double> xx, depth;
+    DevBuf<int> st;
+    BN_TRY(xx.alloc(ctx, (size_t)m->C));
+    BN_TRY(depth.alloc(ctx, 1));
+    BN_TRY(st.alloc(ctx, 1));
+    const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
+    BN_LAUNCH(ctx, k_colsums, blocks, 256, 0, m->C, m->colptr, m->val, xx.p);
+    BN_TRY(bn_allreduce(ctx, xx.p, m->C, 0)); // per-cell totals over gene shards
+    BN_LAUNCH(ctx, k_mean_depth, 1, 1024, 0, m->C, xx.p, b.p, depth.p, st.p);
+    // rowMeans(Data / colSums): the MME mean pass with the column sums in the place of BETA, then * Mean_depth
+    BN_TRY(launch_row_moments(ctx, m, 1, xx.p, nullptr, olam.p, nullptr, nullptr));
+    BN_LAUNCH(ctx, k_scale_vec, (unsigned)((m->G + 255) / 256), 256, 0, m->G, olam.p, depth.p);
+    int h = 0;
+    BN_CUDA(ctx, cudaMemcpyAsync(&h, st.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BN_TRY(bn_sync(ctx));
+    if (h) return bn_fail(ctx, BN_ERR_INVALID, "SyntheticControl: a cell has no counts (colSums == 0 makes every lambda NaN in the reference)");
+    if (onc.p) {
+        const int grid = (int)std::min<int64_t>((m->G * m->C + 255) / 256, 148 * 32);
+        BN_LAUNCH(ctx, k_synthetic_control, grid, 256, 0, m->G, m->C, olam.p, b.p, seed, m->gene0, m->cell0, onc.p);
+    }
+    BN_TRY(olam.commit(ctx));
+    BN_TRY(onc.commit(ctx));
+    return bn_sync(ctx);
 }
 
 // ---------------------------------------------------------------------------------

@@ -111,7 +111,7 @@ __device__ __forceinline__ double bn_rnorm(Philox &g)
 }
 
 // Gamma(shape a, scale 1), Marsaglia & Tsang (2000); a < 1 boosted by U^(1/a).
-__device__ double bn_rgamma(Philox &g, double a)
+static __device__ double bn_rgamma(Philox &g, double a)
 {
     double boost = 1.0;
     if (a < 1.0) {
@@ -135,7 +135,7 @@ __device__ double bn_rgamma(Philox &g, double a)
 }
 
 // Poisson(lam): sequential inversion below 10, Hoermann's PTRS (1993) above.
-__device__ double bn_rpois(Philox &g, double lam)
+static __device__ double bn_rpois(Philox &g, double lam)
 {
     if (!(lam > 0.0)) return 0.0;
     if (lam < 10.0) {
@@ -199,7 +199,7 @@ __device__ __forceinline__ double bn_nb_draw(const NBParams &P, Philox &g)
 
 // ---- binomial(n, p) for DownSampling ----------------------------------------------------------
 // Inversion from 0 for n*min(p,1-p) < 30 (counts are small and beta ~ 0.06), Hoermann's BTRS above.
-__device__ double bn_rbinom(Philox &g, double n, double pp)
+static __device__ double bn_rbinom(Philox &g, double n, double pp)
 {
     if (!(n > 0.0) || !(pp > 0.0)) return 0.0;
     if (pp >= 1.0) return n;
@@ -294,7 +294,7 @@ __device__ __forceinline__ float bn_rnormf(Philox &g)
 // repeated in double only when the float comparison is closer than its own rounding error bound
 // (probability ~1e-4), so an FP64 logarithm almost never stalls the 31 other lanes of the warp.
 //   log v = 3 log1p(cx),  1 - v = -(3t + 3t^2 + t^3)  (t = cx): no cancellation against 1
-__device__ float bn_rgammaf(Philox &g, float a)
+static __device__ float bn_rgammaf(Philox &g, float a)
 {
     float boost = 1.0f;
     if (a < 1.0f) {
@@ -337,7 +337,7 @@ __device__ __forceinline__ float bn_stirling_remf(float k)
 //   -lam + k log lam - log k! = lam (delta - (1 + delta) log1p(delta)) - 0.5 log(2 pi k) - rem(k),
 //   delta = (k - lam)/lam,
 // whose rounding error is ~1e-7 |k - lam|, and repeated in double only inside that error band.
-__device__ float bn_rpoisf(Philox &g, float lam)
+static __device__ float bn_rpoisf(Philox &g, float lam)
 {
     if (!(lam > 0.0f)) return 0.0f;
     if (lam < 10.0f) {

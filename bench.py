@@ -135,6 +135,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def traffic_from_profiles(config, phase, launches):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the phase's dominant kernel, per launch, from the
+    committed `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py)."""
+    try:
+        t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        e = t[str(config)][phase]
+        return {"bytes_per_launch": e["bytes_per_launch"], "kernel": e["kernel"], "source": e["source"]}
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # the GPU arm
 # ----------------------------------------------------------------------------------------------
@@ -312,13 +323,27 @@ def run_ours(args):
     rho = sum(m.nnz for m in Ms) / float(sum(G * m.C for m in Ms))
     post_bytes = sum(G * m.C for m in Ms) * (8.0 * S + 12.0 * rho) + (G * C * (8.0 + 12.0 * rho) if want_mean_too else 0)
     post_s = phase["posterior"]
-    roof_post = {"kernel": "k_posterior<%s>" % out_kind, "bound": "hbm", "achieved": post_bytes / post_s / 1e9,
+    # write-only ceilings of this device, measured live (bn_debug_write_peak): one linear stream, and the
+    # dim = c(G, C, S) plane pattern of the 3-D output at 1 KB per plane visit (what k_post_sample issues)
+    wp = {}
+    for nm, planes, run in (("linear", 1, 1), ("planes_S_1KB_runs", max(S, 1), 4)):
+        v = CT.c_double()
+        ctx.check(lib.bn_debug_write_peak(ctx.h, 2 << 30, planes, run, CT.byref(v)))
+        wp[nm] = v.value
+    post_kernel = {"mode": "k_posterior<mode>", "mean": "k_posterior<mean>",
+                   "sample": "k_post_sample (+ k_post_sample_table, k_post_sample_heavy)"}[out_kind]
+    post_launches = sum(-(-m.C // tile_cols) for m in Ms) * (2 if want_mean_too else 1)
+    roof_post = {"kernel": post_kernel, "bound": "hbm", "achieved": post_bytes / post_s / 1e9,
                  "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-                 "frac": post_bytes / post_s / 1e9 / hbm_peak, "traffic": None, "ms": post_s * 1e3,
-                 "algorithmic_bytes": post_bytes}
+                 "frac": post_bytes / post_s / 1e9 / hbm_peak,
+                 "traffic": traffic_from_profiles(args.config, "posterior", post_launches), "ms": post_s * 1e3,
+                 "algorithmic_bytes": post_bytes, "launches_per_step": post_launches,
+                 "write_only_peak_GBs": wp,
+                 "frac_of_write_only_peak": post_bytes / post_s / 1e9 / (wp["planes_S_1KB_runs"] if out_kind == "sample" else wp["linear"])}
     roof_fit = {"kernel": "k_fit_size", "bound": "fp64", "achieved": fit_flops / fit_s / 1e12,
                 "peak": fp64_peak.value / 1e12, "peak_source": "measured DFMA micro-benchmark (bn_debug_fp64_peak)",
-                "unit": "TFLOP/s", "frac": fit_flops / fit_s / fp64_peak.value, "traffic": None, "ms": fit_s * 1e3,
+                "unit": "TFLOP/s", "frac": fit_flops / fit_s / fp64_peak.value,
+                "traffic": traffic_from_profiles(args.config, "fit", len(Ms)), "ms": fit_s * 1e3,
                 "likelihood_terms_per_s": (dense_terms + nz_terms) / fit_s, "evaluations": evals}
     dominant = roof_fit if fit_s >= post_s else roof_post
 

@@ -210,6 +210,21 @@ BN_API int bn_post_sample(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, 
 BN_API int bn_downsample(bn_ctx *ctx, int64_t G, int64_t C, const double *Data, const double *BETA_vec,
                          uint64_t seed, double *out);
 
+/* ---- BetaFun  (R/PRIOR_FUNCTIONS.R:30-71) ------------------------------------------- */
+/* Capture efficiencies from the library sizes of a robust gene subset: genes whose largest
+ * log(normalised count + 1) lies below median + 3 MAD (over all cells) and that are zero in
+ * fewer than 35 % of the cells.  BETA[C]; selected[G] (0/1, may be NULL);
+ * stats[4*G] = {median | mad | max | zero fraction} per gene (may be NULL; median/mad/max are NaN
+ * for genes that fail the zero-fraction test: they are never evaluated). */
+BN_API int bn_beta_fun(bn_ctx *ctx, bn_mat *m, double MeanBETA, double *BETA, int32_t *selected, double *stats);
+
+/* ---- SyntheticControl  (R/synthetic_controls.r:57-70) ------------------------------ */
+/* lambda[G] = rowMeans(t(t(Data)/colSums(Data)) * mean(colSums(Data)/BETA_vec));
+ * N_c[G x C, column-major] ~ DownSampling(rpois(lambda_i), BETA_j).  N_c may be NULL (lambda only).
+ * Fails with BN_ERR_INVALID when a cell has no counts (the reference returns NaN everywhere). */
+BN_API int bn_synthetic_control(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, uint64_t seed, double *lambda,
+                                double *N_c);
+
 /* ---- benchmarking helpers ---------------------------------------------------------- */
 /* Forget the gene-major twin of the matrix so the next per-gene stage rebuilds it (bench.py
  * times the build inside every step). */

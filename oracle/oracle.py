@@ -322,6 +322,41 @@ def DownSampling(Data, BETA_vec, seed=1):
     return out.reshape(Cn, G).T
 
 
+def BetaFun(Data, MeanBETA):
+    """R/PRIOR_FUNCTIONS.R:30-71 restated with numpy on a dense matrix (the reference's own formulation:
+    dense `apply` loops): returns BETA, the selected row indices and the per-gene statistics."""
+    A = np.asarray(Data, _D)
+    xx = A.sum(axis=0)
+    norm = (A / xx[None, :]) * xx.mean()                       # :39
+    L = np.log(norm + 1.0)
+    med = np.median(L, axis=1)                                   # :44-46
+    mad = 1.4826 * np.median(np.abs(L - med[:, None]), axis=1)   # :47-49 stats::mad
+    mx = L.max(axis=1)                                           # :51
+    dropout = (A == 0).mean(axis=1)                              # :53-55
+    sel = np.nonzero((mx < med + 3 * mad) & (dropout < 0.35))[0]  # :52, :56
+    t = A[sel, :].sum(axis=0)                                    # :59
+    beta = t / t.mean() * MeanBETA                               # :60
+    if (beta >= 1).any():                                        # :61-63
+        beta[beta >= 1] = beta[beta < 1].max()
+    if (beta <= 0).any():                                        # :64-66
+        beta[beta <= 0] = beta[beta > 0].min()
+    return {"BETA": beta, "Selected_genes": sel, "stats": {"median": med, "mad": mad, "max": mx, "dropout": dropout}}
+
+
+def SyntheticControl(Data, BETA_vec, seed=1):
+    """R/synthetic_controls.r:57-70 restated with numpy (dense input):
+    Mean_depth = mean(colSums/BETA); lambda = rowMeans(t(t(Data)/colSums) * Mean_depth);
+    N_c = DownSampling(rpois(G*C, lambda), BETA)."""
+    A = np.asarray(Data, _D)
+    b = np.asarray(BETA_vec, _D)
+    cs = A.sum(axis=0)
+    mean_depth = np.mean(cs / b)
+    lam = ((A / cs[None, :]) * mean_depth).mean(axis=1)
+    rng = np.random.default_rng(seed)
+    N = rng.poisson(np.repeat(lam[:, None], A.shape[1], axis=1)).astype(_D)
+    return {"N_c": rng.binomial(N.astype(np.int64), b[None, :]).astype(_D), "beta_c": b, "lambda": lam}
+
+
 # --------------------------------------------------------------------------------------
 # R-level orchestration restated
 # --------------------------------------------------------------------------------------

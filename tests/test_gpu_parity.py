@@ -536,19 +536,13 @@ def test_baynorm_conditions_ll_and_gg(bn, ctx, oracle, small):
 
 
 # ------------------------------------------------------------------------ gene-sharded path
-def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
-    """Two gene shards, each with its own context and the all-reduce hook installed (two host threads
-    on one GPU; the hook is a barrier + reduce over the two device buffers).  BETA, MME, BB_SIZE are
-    bit-identical to the unsharded run, the adjusted size agrees to the last few ulps."""
+def _run_gene_sharded(bn, Mo, X, world, work):
+    """Runs work(context, shard matrix, rank) on `world` gene shards, each with its own context and the
+    all-reduce hook installed (host threads on one GPU; the hook is a barrier + reduce over the shards'
+    device buffers).  Returns the list of results."""
     import threading
     torch = pytest.importorskip("torch")
     from baynorm_b200 import dist
-    X = small["X"]
-    Mo = small["Mo"]
-    Mfull = bn.Check_input(X, ctx)
-    beta_full = bn.api._default_beta(Mfull)
-    full = bn.Prior_fun(Mfull, beta_full, verbose=False)
-    world = 2
     bounds = dist.balanced_gene_blocks(np.diff(Mo.p[:1]).sum() + (X > 0).sum(axis=1), world, n_cells=Mo.C)
     barrier = threading.Barrier(world)
     slots = [None] * world
@@ -579,9 +573,7 @@ def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
             G, Cn, p, i, x = dist.split_csc_rows(Mo.G, Mo.C, Mo.p, Mo.i, Mo.x, g0, g1)
             M = bn.DeviceMatrix.from_csc(c, G, Cn, p, i, x)
             M.set_origin(gene0=g0)
-            beta = bn.api._default_beta(M)
-            P = bn.Prior_fun(M, beta, verbose=False)
-            results[rank] = (beta, P)
+            results[rank] = work(c, M, rank, g0)
             M.close()
             c.close()
         except Exception as e:      # pragma: no cover
@@ -594,6 +586,24 @@ def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
     for t in th:
         t.join(timeout=120)
     assert not errors, errors
+    return results
+
+
+def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
+    """Two gene shards: BETA, MME, BB_SIZE are bit-identical to the unsharded run, the adjusted size agrees
+    to the last few ulps."""
+    X = small["X"]
+    Mo = small["Mo"]
+    Mfull = bn.Check_input(X, ctx)
+    beta_full = bn.api._default_beta(Mfull)
+    full = bn.Prior_fun(Mfull, beta_full, verbose=False)
+    world = 2
+
+    def work(c, M, rank, g0):
+        beta = bn.api._default_beta(M)
+        return beta, bn.Prior_fun(M, beta, verbose=False)
+
+    results = _run_gene_sharded(bn, Mo, X, world, work)
     for r in range(world):
         assert np.array_equal(results[r][0], beta_full)
     cat = lambda f: np.concatenate([f(results[r][1]) for r in range(world)])
@@ -601,6 +611,31 @@ def test_gene_sharded_prior_matches_unsharded(bn, ctx, oracle, small):
     assert np.array_equal(cat(lambda P: P["MME_prior"]["MME_SIZE"]), full["MME_prior"]["MME_SIZE"])
     assert np.array_equal(cat(lambda P: P["BB_prior"]["BB_SIZE"]), full["BB_prior"]["BB_SIZE"])
     assert rel_err(cat(lambda P: P["MME_SIZE_adjust"]), full["MME_SIZE_adjust"]).max() < 1e-12
+
+
+def test_gene_sharded_betafun_and_controls(bn, ctx, oracle, dense50):
+    """BetaFun and SyntheticControl on two gene shards: the column sums cross the shards through the
+    all-reduce hook; selection, BETA, lambda and the control counts equal the unsharded run."""
+    X = dense50["X"].copy()
+    X[:, X.sum(axis=0) == 0] += 1.0
+    Mo = oracle.CSC.from_dense(X)
+    full = bn.BetaFun(X, 0.06, ctx=ctx)
+    ctl = bn.SyntheticControl(X, dense50["beta"], seed=5, ctx=ctx)
+    assert len(full["Selected_genes"]) > 0
+
+    def work(c, M, rank, g0):
+        bf = bn.BetaFun(M, 0.06, ctx=c)
+        sc = bn.SyntheticControl(M, dense50["beta"], seed=5, ctx=c)
+        return bf["BETA"], np.asarray(bf["Selected_genes"]) + g0, sc["lambda"], sc["N_c"]
+
+    res = _run_gene_sharded(bn, Mo, X, 2, work)
+    for r in range(2):
+        np.testing.assert_allclose(res[r][0], full["BETA"], rtol=1e-13)
+    assert np.array_equal(np.concatenate([res[r][1] for r in range(2)]), np.asarray(full["Selected_genes"]))
+    np.testing.assert_allclose(np.concatenate([res[r][2] for r in range(2)]), ctl["lambda"], rtol=1e-13)
+    # the draws are keyed by global gene / cell indices: identical whenever lambda is bit-identical
+    same = np.concatenate([res[r][2] for r in range(2)]) == ctl["lambda"]
+    assert np.array_equal(np.concatenate([res[r][3] for r in range(2)])[same], ctl["N_c"][same])
 
 
 # ------------------------------------------------------------------------ edge cases
@@ -721,3 +756,66 @@ def test_posterior_samples_every_path(bn, ctx, oracle):
     # purity across S and column blocks holds on every path
     assert np.array_equal(bn.Main_NB_Bay(M, beta, size, mu, S=7, seed=2024), d[:, :, :7])
     assert np.array_equal(bn.Main_NB_Bay(M, beta, size, mu, S=S, seed=2024, col0=17, ncol=40), d[:, 17:57, :])
+
+
+# ------------------------------------------------------------------------ SyntheticControl
+def test_synthetic_control(bn, ctx, oracle, small):
+    """R/synthetic_controls.r:57-70: lambda against the numpy restatement (closed form), the counts against
+    their exact law -- rbinom(rpois(lambda_i), beta_j) is Poisson(lambda_i beta_j)."""
+    from scipy.stats import chi2, poisson
+    X, beta = small["X"][:150, :200].copy(), small["beta"][:200].copy()
+    X[:, X.sum(axis=0) == 0] += 1.0                                  # every cell needs a count
+    out = bn.SyntheticControl(X, beta, seed=77, ctx=ctx)
+    ref = oracle.SyntheticControl(X, beta, seed=1)
+    np.testing.assert_allclose(out["lambda"], ref["lambda"], rtol=1e-12)
+    assert np.array_equal(out["beta_c"], beta)
+    N = out["N_c"]
+    assert N.shape == X.shape and np.array_equal(N, np.floor(N)) and (N >= 0).all()
+    assert np.array_equal(bn.SyntheticControl(X, beta, seed=77, ctx=ctx)["N_c"], N)          # pure function of the seed
+    assert not np.array_equal(bn.SyntheticControl(X, beta, seed=78, ctx=ctx)["N_c"], N)
+    lam = out["lambda"][:, None] * beta[None, :]
+    z = (N.sum(axis=1) - lam.sum(axis=1)) / np.sqrt(lam.sum(axis=1) + 1e-300)               # per gene
+    assert np.abs(z).max() < 5 and abs(z.mean()) < 4 / np.sqrt(z.size)
+    zc = (N.sum(axis=0) - lam.sum(axis=0)) / np.sqrt(lam.sum(axis=0))                         # per cell
+    assert np.abs(zc).max() < 5
+    rng = np.random.default_rng(2)                                                           # pooled randomised PIT
+    u = poisson.cdf(N - 1, lam) + (poisson.cdf(N, lam) - poisson.cdf(N - 1, lam)) * rng.random(N.shape)
+    h, _ = np.histogram(u.ravel(), bins=50, range=(0, 1))
+    stat = float(((h - u.size / 50) ** 2 / (u.size / 50)).sum())
+    assert stat < chi2.ppf(1 - 1e-6, 49), stat
+    # the oracle's own draws follow the same law
+    No = ref["N_c"]
+    zo = (No.sum(axis=1) - (ref["lambda"][:, None] * beta[None, :]).sum(axis=1)) / np.sqrt(lam.sum(axis=1) + 1e-300)
+    assert np.abs(zo).max() < 5
+    Xz = X.copy()
+    Xz[:, 3] = 0.0
+    with pytest.raises(bn.BayNormError):
+        bn.SyntheticControl(Xz, beta, ctx=ctx)
+
+
+# ------------------------------------------------------------------------ BetaFun
+@pytest.mark.parametrize("which", ["fixture", "dense_even", "dense_odd"])
+def test_beta_fun(bn, ctx, oracle, fixture_data, which):
+    """R/PRIOR_FUNCTIONS.R:30-71 against the dense numpy restatement: zero fractions, the order statistics of
+    the genes that can be selected, the selected set and BETA."""
+    if which == "fixture":
+        X = fixture_data["inputdata"]                                # 20 x 74, the reference's own example call
+    else:
+        rng = np.random.default_rng(21)
+        G, Cn = 260, (150 if which == "dense_even" else 151)
+        mu = rng.lognormal(1.5, 1.2, G)
+        X = rng.poisson(rng.gamma(2.0, mu[:, None] / 2.0, (G, Cn)) * rng.uniform(0.5, 1.5, Cn)[None, :]).astype(np.float64)
+        X[:, X.sum(axis=0) == 0] += 1.0
+    got = bn.BetaFun(X, 0.06, ctx=ctx, with_stats=True)
+    ref = oracle.BetaFun(X, 0.06)
+    np.testing.assert_allclose(got["stats"]["dropout"], ref["stats"]["dropout"], rtol=0, atol=0)
+    cand = ref["stats"]["dropout"] < 0.35
+    assert cand.sum() > 3, "test matrix has no candidate genes"
+    for k in ("median", "mad", "max"):
+        np.testing.assert_allclose(got["stats"][k][cand], ref["stats"][k][cand], rtol=1e-13, atol=1e-15, err_msg=k)
+        assert np.isnan(got["stats"][k][~cand]).all()
+    assert np.array_equal(np.asarray(got["Selected_genes"]), ref["Selected_genes"])
+    assert 0 < len(ref["Selected_genes"]) < X.shape[0]
+    np.testing.assert_allclose(got["BETA"], ref["BETA"], rtol=1e-12)
+    assert (got["BETA"] > 0).all() and (got["BETA"] < 1).all()
+    assert abs(got["BETA"].mean() - 0.06) < 1e-12 or (ref["BETA"] != ref["BETA"].clip(0, 1)).any()
