@@ -71,6 +71,8 @@ SIGNATURES = {
     "bn_gradient_nb_2d": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _VP]),
     "bn_fit_opts_default": (None, [C.POINTER(FitOpts)]),
     "bn_fit_size": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _D, _D, C.POINTER(FitOpts), _VP, _VP, _VP]),
+    "bn_fit_size_mu": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _D, _D, _D, _D, C.POINTER(FitOpts), _VP, _VP, _VP, _VP]),
+    "bn_vec_range": (C.c_int, [_VP, _VP, _I64, _VP]),
     "bn_adjust_size": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _VP]),
     "bn_prior": (C.c_int, [_VP, _VP, _VP, C.c_int, C.POINTER(FitOpts), C.POINTER(PriorOut)]),
     "bn_post_mean": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _VP]),

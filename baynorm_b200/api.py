@@ -439,9 +439,8 @@ def BB_Fun(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, MU_lower=0.01, MU_u
            SIZE_upper=30, parallel=False, NCores=5, FIX_MU=True, GR=False, method="spg", ctx=None,
            return_info=False):
     """R/PRIOR_FUNCTIONS.R:380-549.  `parallel`/`NCores` are accepted and ignored: the fit of
-    all genes is one kernel launch."""
-    if not FIX_MU:
-        raise NotImplementedError("FIX_MU=FALSE (2-D size/mu fit) is a 'next' row (SURVEY.md 8(f) rank 3)")
+    all genes is one kernel launch.  FIX_MU=False returns the G x 2 matrix (size, mu) of the
+    reference (:543-546), fitted in the box of its parallel=TRUE branch (:414-419)."""
     M = Check_input(Data, ctx)
     ctx = M.ctx
     b, mu0, s0 = _vec(BETA_vec, M.C, "BETA_vec"), _vec(INITIAL_MU_vec, M.G), _vec(INITIAL_SIZE_vec, M.G)
@@ -449,6 +448,13 @@ def BB_Fun(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, MU_lower=0.01, MU_u
     conv = np.zeros(M.G, np.int32)
     nfe = np.zeros(M.G, np.int32)
     o = _fit_opts(GR, method)
+    if not FIX_MU:
+        mu_out = np.zeros(M.G, _F64)
+        ctx.check(ctx.lib.bn_fit_size_mu(ctx.h, M.h, _ptr(b), _ptr(mu0), _ptr(s0), float(SIZE_lower), float(SIZE_upper),
+                                         float(MU_lower), float(MU_upper), C.byref(o), _ptr(out), _ptr(mu_out),
+                                         _ptr(conv), _ptr(nfe)))
+        par = np.asfortranarray(np.stack([out, mu_out], axis=1))        # colnames c('size', 'mu')
+        return (par, conv, nfe) if return_info else par
     ctx.check(ctx.lib.bn_fit_size(ctx.h, M.h, _ptr(b), _ptr(mu0), _ptr(s0), float(SIZE_lower), float(SIZE_upper),
                                   C.byref(o), _ptr(out), _ptr(conv), _ptr(nfe)))
     return (out, conv, nfe) if return_info else out
@@ -466,12 +472,30 @@ def AdjustSIZE_fun(BB_SIZE, MME_MU, MME_SIZE, ctx=None):
 
 def Prior_fun(Data, BETA_vec, parallel=True, NCores=5, FIX_MU=True, GR=False, BB_SIZE=True, verbose=True,
               method="spg", ctx=None, return_info=False):
-    """R/PRIOR_FUNCTIONS.R:241-311 in one native call (bn_prior)."""
-    if not FIX_MU:
-        raise NotImplementedError("FIX_MU=FALSE (2-D size/mu fit) is a 'next' row (SURVEY.md 8(f) rank 3)")
+    """R/PRIOR_FUNCTIONS.R:241-311 in one native call (bn_prior).  FIX_MU=False runs the MME step natively,
+    then the 2-D fit in the box the reference builds from the MME estimates (:275-279) and the size
+    adjustment on BB_prior[, 1] (:291-296); BB_prior is then the G x 2 (size, mu) matrix."""
     M = Check_input(Data, ctx)
     ctx = M.ctx
     b = _vec(BETA_vec, M.C, "BETA_vec")
+    if not FIX_MU and BB_SIZE:
+        base = Prior_fun(M, b, FIX_MU=True, BB_SIZE=False, verbose=False, ctx=ctx, return_info=True)
+        MU, SIZE = base["MME_prior"]["MME_MU"], base["MME_prior"]["MME_SIZE"]
+        rng = np.zeros(2, _F64)
+        ctx.check(ctx.lib.bn_vec_range(ctx.h, _ptr(MU), M.G, _ptr(rng)))      # min / max over all gene shards
+        if verbose:
+            print("Start optimization using spg from BB package.\nThis part may be time-consuming.")
+        par, conv, nfe = BB_Fun(M, b, MU, SIZE, MU_lower=rng[0], MU_upper=rng[1], SIZE_lower=base["_info"]["size_lower"],
+                                SIZE_upper=base["_info"]["size_upper"], FIX_MU=False, GR=GR, method=method, ctx=ctx,
+                                return_info=True)
+        ADJ = AdjustSIZE_fun(np.ascontiguousarray(par[:, 0]), MU, SIZE, ctx=ctx)
+        if verbose:
+            print("Prior estimation has completed!")
+        out = {"MME_prior": base["MME_prior"], "BB_prior": {"size": par[:, 0], "mu": par[:, 1]}, "MME_SIZE_adjust": ADJ,
+               "BETA_vec": base["BETA_vec"]}
+        if return_info:
+            out["_info"] = dict(base["_info"], conv=conv, nfeval=nfe, mu_lower=float(rng[0]), mu_upper=float(rng[1]))
+        return out
     MU, SIZE = np.zeros(M.G, _F64), np.zeros(M.G, _F64)
     BB, ADJ = (np.zeros(M.G, _F64), np.zeros(M.G, _F64)) if BB_SIZE else (None, None)
     conv, nfe = np.zeros(M.G, np.int32), np.zeros(M.G, np.int32)

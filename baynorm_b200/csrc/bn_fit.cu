@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
                 const double x = (double)(uint32_t)e0;
                 kk += x * (g.lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
                 const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
-                atomicAdd(&hist[xi - 1], 1u);
+                if (xi > 0) atomicAdd(&hist[xi - 1], 1u); // an explicitly stored zero has no lgamma term
                 xm = max(xm, xi);
             }
             atomicMax(&xmax_all[grp], xm);
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(256, MINB)
                 const double x = (double)(uint32_t)e0;
                 kk += x * (lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
                 const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
-                atomicAdd(&sl.tail[xi - 1], 1u);
+                if (xi > 0) atomicAdd(&sl.tail[xi - 1], 1u); // an explicitly stored zero has no lgamma term
                 xm = max(xm, xi);
             }
             atomicMax(&xmax_sh, xm);
@@ -906,6 +906,319 @@ __global__ void __cluster_dims__(FIT_CL, 1, 1) __launch_bounds__(FIT_CL_THREADS,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// FIX_MU = FALSE (R/PRIOR_FUNCTIONS.R:414-419, :457-470): BB::spg over par = (size, mu) in the box
+// [SIZE_lower, SIZE_upper] x [MU_lower, MU_upper], objective MarginalF_NB_2D
+// (src/bayNorm_main.cpp:948-965), gradient by forward differences (eps = 1e-7 per coordinate) or
+// GradientFun_NB_2D (:993-1013) when GR = TRUE.  Spg2State is orc_spg (oracle/baynorm_oracle.c) for
+// n = 2 as a resumable state machine; one 256-thread CTA works on one gene at a time.
+// The likelihood is the same expression as in the 1-D fit with mu a variable: the only mu-dependent
+// constant is Kc = X log mu + K0, X = sum x, K0 = sum x log beta_j - sum lgamma(x+1).
+// ---------------------------------------------------------------------------------
+struct Spg2State {
+    enum { INIT_F = 0, INIT_G = 1, LS = 2, GRAD = 3 };
+    double lo[2], hi[2], par[2], g[2], pnew[2], gnew[2], d[2], pbest[2];
+    double lastfv[16];
+    double f, fbest, fchg, pginfn, lambda, gtd, fmaxv, alpha;
+    int phase, gi, iter, feval, lsflag, M;
+    bool ls_first;
+    // request: evaluate at next[]; kind 0 = -l, 1 = -dl/dsize, 2 = -dl/dmu
+    double next[2];
+    int kind, conv;
+
+    __device__ void init(const double *par0, const double *lower, const double *upper, const FitOpts &o)
+    {
+        M = o.M > 16 ? 16 : (o.M < 1 ? 1 : o.M);
+#pragma unroll
+        for (int i = 0; i < 16; i++) lastfv[i] = -1e99;
+        for (int i = 0; i < 2; i++) {
+            lo[i] = lower[i];
+            hi[i] = upper[i];
+            par[i] = proj(par0[i], lo[i], hi[i]);
+            pbest[i] = par[i];
+            next[i] = par[i];
+        }
+        iter = feval = 0;
+        lsflag = -1;
+        fchg = INFINITY;
+        lambda = 1.0;
+        phase = INIT_F;
+        kind = 0;
+        conv = 0;
+    }
+    // ask for gradient component gi at point p (held in `at`)
+    __device__ __forceinline__ void ask_grad(const double *at, const FitOpts &o)
+    {
+        next[0] = at[0];
+        next[1] = at[1];
+        if (o.use_gradient) kind = 1 + gi;
+        else {
+            kind = 0;
+            next[gi] = at[gi] + o.eps;
+        }
+    }
+    __device__ bool finish()
+    {
+        if (lsflag <= 0) conv = 0;
+        else conv = (lsflag == 1) ? 3 : (lsflag == 2) ? 2 : (lsflag == 3) ? 4 : 5;
+        next[0] = pbest[0];
+        next[1] = pbest[1];
+        return false;
+    }
+    __device__ void proj_grad_norm()
+    {
+        pginfn = 0.0;
+        for (int i = 0; i < 2; i++) pginfn = fmax(pginfn, fabs(proj(par[i] - g[i], lo[i], hi[i]) - par[i]));
+    }
+    __device__ bool enter_iter(const FitOpts &o)
+    {
+        if (!(pginfn > o.gtol && iter <= o.maxit && fchg > o.ftol)) {
+            const bool r = finish();
+            if (lsflag <= 0 && iter >= o.maxit) conv = 1;
+            return r;
+        }
+        iter++;
+        gtd = 0.0;
+        for (int i = 0; i < 2; i++) {
+            d[i] = proj(par[i] - lambda * g[i], lo[i], hi[i]) - par[i];
+            gtd += g[i] * d[i];
+        }
+        if (isinf(gtd)) {
+            lsflag = 4;
+            return finish();
+        }
+        fmaxv = lastfv[0];
+#pragma unroll
+        for (int i = 1; i < 16; i++)
+            if (i < M && lastfv[i] > fmaxv) fmaxv = lastfv[i];
+        alpha = 1.0;
+        for (int i = 0; i < 2; i++) pnew[i] = next[i] = par[i] + alpha * d[i];
+        phase = LS;
+        ls_first = true;
+        kind = 0;
+        return true;
+    }
+    __device__ bool step(double v, const FitOpts &o)
+    {
+        const double lmin = 1e-30, lmax = 1e30;
+        switch (phase) {
+        case INIT_F:
+            f = v;
+            feval++;
+            if (f != f || isinf(f)) {
+                conv = 3;
+                next[0] = par[0];
+                next[1] = par[1];
+                return false;
+            }
+            fbest = f;
+            phase = INIT_G;
+            gi = 0;
+            ask_grad(par, o);
+            return true;
+        case INIT_G:
+            g[gi] = o.use_gradient ? v : (v - f) / o.eps;
+            if (++gi < 2) {
+                ask_grad(par, o);
+                return true;
+            }
+            if (g[0] != g[0] || g[1] != g[1]) {
+                conv = 4;
+                next[0] = par[0];
+                next[1] = par[1];
+                return false;
+            }
+            lastfv[0] = f;
+            proj_grad_norm();
+            if (pginfn != 0.0) lambda = fmin(lmax, fmax(lmin, 1.0 / pginfn));
+            return enter_iter(o);
+        case LS: {
+            const double fnew = v;
+            feval++;
+            lsflag = 0;
+            if (fnew != fnew) {
+                lsflag = 1;
+                return finish();
+            }
+            if (!ls_first && feval > o.maxfeval) {
+                lsflag = 2;
+                return finish();
+            }
+            ls_first = false;
+            if (fnew > fmaxv + 1e-4 * alpha * gtd) { // nonmonotone Armijo test failed: backtrack
+                if (alpha <= 0.1) alpha = alpha / 2;
+                else {
+                    double atemp = -(gtd * alpha * alpha) / (2 * (fnew - f - alpha * gtd));
+                    if (atemp < 0.1 || atemp > 0.9 * alpha) atemp = alpha / 2;
+                    alpha = atemp;
+                }
+                for (int i = 0; i < 2; i++) pnew[i] = next[i] = par[i] + alpha * d[i];
+                kind = 0;
+                return true;
+            }
+            fchg = fabs(f - fnew);
+            f = fnew;
+            const int slot = iter % M;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i == slot) lastfv[i] = f;
+            phase = GRAD;
+            gi = 0;
+            ask_grad(pnew, o);
+            return true;
+        }
+        default: { // GRAD
+            gnew[gi] = o.use_gradient ? v : (v - f) / o.eps;
+            if (++gi < 2) {
+                ask_grad(pnew, o);
+                return true;
+            }
+            if (gnew[0] != gnew[0] || gnew[1] != gnew[1]) {
+                lsflag = 3;
+                return finish();
+            }
+            double sts = 0.0, yty = 0.0;
+            for (int i = 0; i < 2; i++) {
+                const double sv = pnew[i] - par[i], yv = gnew[i] - g[i];
+                sts += sv * sv;
+                yty += yv * yv;
+                par[i] = pnew[i];
+                g[i] = gnew[i];
+            }
+            lambda = (sts == 0.0 || yty == 0.0) ? lmax : fmin(lmax, fmax(lmin, sqrt(sts / yty)));
+            proj_grad_norm();
+            if (f < fbest) {
+                fbest = f;
+                pbest[0] = pnew[0];
+                pbest[1] = pnew[1];
+            }
+            return enter_iter(o);
+        }
+        }
+    }
+};
+
+// d l / d mu = sum_j size (x_j - mu beta_j) / (mu (mu beta_j + size))       (GradientFun_NB_2D, :1004)
+template <int TPG> __device__ double nb_loglik_grad_mu(const FitGene &g, double phi, double *scratch, int tid)
+{
+    const double mu = g.mu;
+    double acc = 0.0;
+    for (int64_t j = tid; j < g.C; j += TPG) {
+        const double mb = mu * __ldg(g.beta + j);
+        acc += (0.0 * phi - mb * phi) / (mu * (mb + phi)); // the x = 0 term of every cell
+    }
+    for (int64_t k = tid; k < g.nnz; k += TPG) {
+        const uint64_t e0 = __ldg(g.nz + k);
+        const double x = (double)(uint32_t)e0;
+        const double mb = mu * __ldg(g.beta + (e0 >> 32));
+        acc += (x * phi) / (mu * (mb + phi)); // (x phi - mb phi) minus the x = 0 term already counted
+    }
+    return bn_group_sum<TPG>(acc, scratch);
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256, 4)
+    k_fit_2d(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
+             const double *__restrict__ beta, const double *__restrict__ logbeta, const double *__restrict__ mu0,
+             const double *__restrict__ size0, const double *__restrict__ box /* lo_size, lo_mu, hi_size, hi_mu, beta_max */,
+             FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out, double *__restrict__ mu_out,
+             int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
+{
+    constexpr int TPG = 256;
+    constexpr int HMAX = FitCfg<TPG>::HMAX;
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    __shared__ double scratch[8];
+    __shared__ unsigned long long next_gene;
+    __shared__ uint32_t hist[HMAX + 1];
+    __shared__ int xmax_sh;
+    bn_log_table_load(tab);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const double lower[2] = {box[0], box[1]}, upper[2] = {box[2], box[3]};
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) next_gene = atomicAdd(queue, 1ULL);
+        __syncthreads();
+        const unsigned long long gq = next_gene;
+        if (gq >= (unsigned long long)G) break;
+        const int64_t gi = (int64_t)gq;
+        FitGene g;
+        const int64_t a = rowptr[gi];
+        g.nz = gm + a;
+        g.nnz = rowptr[gi + 1] - a;
+        g.beta = beta;
+        g.logbeta = logbeta;
+        g.C = C;
+        g.beta_max = box[4];
+        g.tail = hist;
+        // per-gene constants: count histogram -> tail table, X = sum x, K0 = sum x log beta - sum lgamma(x+1)
+        for (int q = tid; q <= HMAX; q += TPG) hist[q] = 0;
+        if (tid == 0) xmax_sh = 0;
+        __syncthreads();
+        double k0 = 0.0, xs = 0.0;
+        int xm = 0;
+        for (int64_t k = tid; k < g.nnz; k += TPG) {
+            const uint64_t e0 = __ldg(g.nz + k);
+            const double x = (double)(uint32_t)e0;
+            if (x > 0.0) { // explicit zeros carry no term
+                k0 += x * __ldg(logbeta + (e0 >> 32)) - lgamma(x + 1.0);
+                xs += x;
+                const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
+                atomicAdd(&hist[xi - 1], 1u);
+                xm = max(xm, xi);
+            }
+        }
+        atomicMax(&xmax_sh, xm);
+        const double K0 = bn_group_sum<TPG>(k0, scratch);
+        const double X = bn_group_sum<TPG>(xs, scratch);
+        __syncthreads();
+        if (tid == 0) { // suffix sum: tail[k] = #{x > k}
+            uint32_t run = hist[HMAX];
+            for (int q = HMAX - 1; q >= 0; q--) {
+                run += hist[q];
+                hist[q] = run;
+            }
+        }
+        __syncthreads();
+        g.n_big = (int)(hist[HMAX]);
+        g.kmax = min(HMAX, xmax_sh);
+        Spg2State st;
+        const double par0[2] = {size0[gi], mu0[gi]};
+        st.init(par0, lower, upper, o);
+        int nfe = 0;
+        bool more = true;
+        while (more) {
+            const double phi = st.next[0];
+            g.mu = st.next[1];
+            double val;
+            if (GRAD && st.kind == 1) val = -nb_loglik_grad<TPG>(g, phi, scratch, tid);
+            else if (GRAD && st.kind == 2) val = -nb_loglik_grad_mu<TPG>(g, phi, scratch, tid);
+            else {
+                // X log mu: dnbinom_mu(x > 0, mu = 0) = 0 gives l = -inf, which spg's line search backs away from
+                g.Kc = (X > 0.0 ? X * log(g.mu) : 0.0) + K0;
+                val = -nb_loglik<TPG>(g, phi, tab, scratch, tid);
+            }
+            nfe++;
+            more = st.step(val, o);
+        }
+        __syncthreads(); // hist is reused by the next gene
+        if (tid == 0) {
+            size_out[gi] = st.next[0];
+            mu_out[gi] = st.next[1];
+            if (conv_out) conv_out[gi] = st.conv;
+            if (nfe_out) nfe_out[gi] = nfe;
+        }
+    }
+}
+
+__global__ void k_fit_box(double lo_size, double lo_mu, double hi_size, double hi_mu, double *__restrict__ box)
+{
+    box[0] = lo_size;
+    box[1] = lo_mu;
+    box[2] = hi_size;
+    box[3] = hi_mu;
+}
+
 // largest beta (decides between the series and the table form of log1p per evaluation)
 __global__ void __launch_bounds__(1024) k_max_vec(int64_t n, const double *__restrict__ v, double *__restrict__ out)
 {
@@ -1141,5 +1454,66 @@ extern "C" int bn_debug_log(bn_ctx *ctx, int which, const double *x, int64_t n, 
     BN_TRY(o.bind(ctx, out, (size_t)n));
     BN_LAUNCH(ctx, k_debug_log, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, which, n, dx.p, o.p);
     BN_TRY(o.commit(ctx));
+    return bn_sync(ctx);
+}
+
+// BB_Fun with FIX_MU = FALSE: one call fits (size, mu) of every gene.
+extern "C" int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const double *INITIAL_MU_vec,
+                              const double *INITIAL_SIZE_vec, double SIZE_lower, double SIZE_upper, double MU_lower,
+                              double MU_upper, const bn_fit_opts *opts, double *size_out, double *mu_out, int32_t *conv,
+                              int32_t *nfeval)
+{
+    if (!ctx || !m || !BETA_vec || !INITIAL_MU_vec || !INITIAL_SIZE_vec || !size_out || !mu_out)
+        return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_fit_size_mu: NULL argument") : BN_ERR_INVALID;
+    if (!m->is_count)
+        return bn_fail(ctx, BN_ERR_NONCOUNT, "the likelihood fit needs non-negative integer counts (dnbinom_mu is 0 elsewhere)");
+    if (!(SIZE_lower > 0.0) || !(SIZE_upper >= SIZE_lower) || !(MU_lower >= 0.0) || !(MU_upper >= MU_lower))
+        return bn_fail(ctx, BN_ERR_INVALID, "bad bounds: size [%g, %g], mu [%g, %g]", SIZE_lower, SIZE_upper, MU_lower, MU_upper);
+    cudaSetDevice(ctx->device);
+    bn_fit_opts od;
+    bn_fit_opts_default(&od);
+    if (opts) od = *opts;
+    if (od.method != BN_FIT_SPG) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "the 2-D fit runs BB::spg only");
+    FitOpts o;
+    o.method = od.method;
+    o.maxfeval = od.maxfeval;
+    o.maxit = od.maxit;
+    o.M = od.M;
+    o.use_gradient = od.use_gradient;
+    o.ftol = od.ftol;
+    o.gtol = od.gtol;
+    o.eps = od.eps;
+    o.xatol = od.xatol;
+    DevIn<double> b, mu0, s0;
+    BN_TRY(b.bind(ctx, BETA_vec, (size_t)m->C));
+    BN_TRY(mu0.bind(ctx, INITIAL_MU_vec, (size_t)m->G));
+    BN_TRY(s0.bind(ctx, INITIAL_SIZE_vec, (size_t)m->G));
+    DevOut<double> so, mo;
+    DevOut<int32_t> co, no;
+    BN_TRY(so.bind(ctx, size_out, (size_t)m->G));
+    BN_TRY(mo.bind(ctx, mu_out, (size_t)m->G));
+    BN_TRY(co.bind(ctx, conv, (size_t)m->G));
+    BN_TRY(no.bind(ctx, nfeval, (size_t)m->G));
+    BN_TRY(bn_mat_ensure_csr(ctx, m));
+    DevBuf<double> lb, box;
+    BN_TRY(lb.alloc(ctx, (size_t)m->C));
+    BN_TRY(box.alloc(ctx, 8));
+    BN_LAUNCH(ctx, k_log_vec, (unsigned)((m->C + 255) / 256), 256, 0, m->C, b.p, lb.p);
+    BN_LAUNCH(ctx, k_fit_box, 1, 1, 0, SIZE_lower, MU_lower, SIZE_upper, MU_upper, box.p);
+    BN_LAUNCH(ctx, k_max_vec, 1, 1024, 0, m->C, b.p, box.p + 4);
+    DevBuf<unsigned long long> q;
+    BN_TRY(q.alloc(ctx, 1));
+    BN_CUDA(ctx, cudaMemsetAsync(q.p, 0, 8, ctx->stream));
+    const int grid = (int)std::min<int64_t>(m->G, (int64_t)ctx->prop.multiProcessorCount * 4);
+    if (o.use_gradient)
+        BN_LAUNCH(ctx, k_fit_2d<true>, grid, 256, 0, m->G, m->C, m->rowptr, m->gm, b.p, lb.p, mu0.p, s0.p, box.p, o, q.p, so.p, mo.p,
+                  co.p, no.p);
+    else
+        BN_LAUNCH(ctx, k_fit_2d<false>, grid, 256, 0, m->G, m->C, m->rowptr, m->gm, b.p, lb.p, mu0.p, s0.p, box.p, o, q.p, so.p, mo.p,
+                  co.p, no.p);
+    BN_TRY(so.commit(ctx));
+    BN_TRY(mo.commit(ctx));
+    BN_TRY(co.commit(ctx));
+    BN_TRY(no.commit(ctx));
     return bn_sync(ctx);
 }

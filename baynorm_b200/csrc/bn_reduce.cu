@@ -480,6 +480,25 @@ int bn_size_bounds_device(bn_ctx *ctx, int64_t G, double *d_size, double *d_mm /
     return BN_OK;
 }
 
+// min and max of the non-NaN entries of a (gene-sharded) vector over ALL shards
+extern "C" int bn_vec_range(bn_ctx *ctx, const double *v, int64_t n, double out[2])
+{
+    if (!ctx || !v || !out || n <= 0) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_vec_range: bad arguments") : BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> in;
+    BN_TRY(in.bind(ctx, v, (size_t)n));
+    DevBuf<double> mm;
+    BN_TRY(mm.alloc(ctx, 2));
+    BN_LAUNCH(ctx, k_minmax_nonan, 1, 1024, 0, n, in.p, mm.p);
+    BN_TRY(bn_allreduce(ctx, mm.p, 2, 1));
+    double h[2];
+    BN_CUDA(ctx, cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    BN_TRY(bn_sync(ctx));
+    out[0] = h[0];
+    out[1] = -h[1];
+    return BN_OK;
+}
+
 int bn_adjust_size_device(bn_ctx *ctx, int64_t G, const double *d_bb, const double *d_ms, double *d_out, double *d_coef)
 {
     DevBuf<double> st;

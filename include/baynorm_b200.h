@@ -167,6 +167,16 @@ BN_API void bn_fit_opts_default(bn_fit_opts *o);
 BN_API int bn_fit_size(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const double *INITIAL_MU_vec,
                        const double *INITIAL_SIZE_vec, double SIZE_lower, double SIZE_upper, const bn_fit_opts *opts,
                        double *size_out, int32_t *conv, int32_t *nfeval);
+/* FIX_MU=FALSE (R/PRIOR_FUNCTIONS.R:414-419, :457-470): BB::spg over par = (size, mu) for every gene,
+ * start (INITIAL_SIZE_vec, INITIAL_MU_vec), box [SIZE_lower, SIZE_upper] x [MU_lower, MU_upper]
+ * (the bounds of the reference's parallel = TRUE branch), objective MarginalF_NB_2D, gradient by
+ * forward differences or GradientFun_NB_2D (opts->use_gradient).  size_out[G], mu_out[G] = BB_opt$par. */
+BN_API int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, const double *INITIAL_MU_vec,
+                          const double *INITIAL_SIZE_vec, double SIZE_lower, double SIZE_upper, double MU_lower,
+                          double MU_upper, const bn_fit_opts *opts, double *size_out, double *mu_out, int32_t *conv,
+                          int32_t *nfeval);
+/* min / max over the non-NaN entries of a vector, across all gene shards (through the all-reduce hook). */
+BN_API int bn_vec_range(bn_ctx *ctx, const double *v, int64_t n, double out[2]);
 
 /* ---- AdjustSIZE_fun  (R/sup_funs.R:27-33) --------------------------------------- */
 /* out[G] = exp(a + b*log(MME_SIZE)), (a,b) = OLS of log BB_SIZE on log MME_SIZE over genes

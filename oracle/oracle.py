@@ -271,6 +271,21 @@ def BB_Fun(M: CSC, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, SIZE_lower, SIZE_
     return out
 
 
+def BB_Fun_2d(A, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, SIZE_lower, SIZE_upper, MU_lower, MU_upper, maxfeval=500):
+    """R/PRIOR_FUNCTIONS.R:457-470 (FIX_MU=FALSE, parallel=TRUE bounds :414-419) on a dense matrix, gene by gene
+    through the restated spg: returns the G x 2 (size, mu) matrix, the convergence codes and the evaluation counts."""
+    A = np.asarray(A, _D)
+    G = A.shape[0]
+    par = np.zeros((G, 2), _D)
+    conv = np.zeros(G, np.int32)
+    cnt = np.zeros((G, 3), np.int32)
+    lo, hi = np.array([SIZE_lower, MU_lower], _D), np.array([SIZE_upper, MU_upper], _D)
+    for g in range(G):
+        p, rc, c = spg_gene_2d([INITIAL_SIZE_vec[g], INITIAL_MU_vec[g]], A[g], BETA_vec, lo, hi, maxfeval)
+        par[g], conv[g], cnt[g] = p, rc, c
+    return par, conv, cnt
+
+
 def AdjustSIZE_fun(BB_SIZE, MME_MU, MME_SIZE):
     """R/sup_funs.R:27-33 (MME_MU is accepted and unused, as upstream)."""
     bb = np.ascontiguousarray(BB_SIZE, _D)

@@ -819,3 +819,73 @@ def test_beta_fun(bn, ctx, oracle, fixture_data, which):
     np.testing.assert_allclose(got["BETA"], ref["BETA"], rtol=1e-12)
     assert (got["BETA"] > 0).all() and (got["BETA"] < 1).all()
     assert abs(got["BETA"].mean() - 0.06) < 1e-12 or (ref["BETA"] != ref["BETA"].clip(0, 1)).any()
+
+
+# ------------------------------------------------------------------------ FIX_MU = FALSE
+@pytest.mark.parametrize("which", ["fixture", "small"])
+def test_fit_2d_against_oracle(bn, ctx, oracle, small, fixture_data, which):
+    """BB_Fun(FIX_MU=FALSE): spg over (size, mu) in the reference's box, against the restated spg running the
+    same algorithm on the CPU.  Like the 1-D fit, the stopping point of a forward-difference spg moves with the
+    last bits of the likelihood, so the assertions are: most genes within 1e-6, all close, and the two stopping
+    points equally good (same likelihood to 1e-9 relative)."""
+    if which == "fixture":
+        X, beta = fixture_data["inputdata"], fixture_data["inputbeta"]
+    else:
+        X, beta = small["X"][:80, :300], small["beta"][:300]
+    Mo = oracle.CSC.from_dense(X)
+    pri = oracle.EstPrior(Mo, beta)
+    size0 = pri["SIZE"].copy()
+    size0[np.isnan(size0)] = np.nanmin(size0)
+    mu0 = pri["MU"]
+    box = dict(SIZE_lower=float(size0.min()), SIZE_upper=float(np.ceil(size0.max())), MU_lower=float(mu0.min()),
+               MU_upper=float(mu0.max()))
+    got, conv, nfe = bn.BB_Fun(X, beta, mu0, size0, FIX_MU=False, ctx=ctx, return_info=True, **box)
+    want, wconv, wcnt = oracle.BB_Fun_2d(X, beta, mu0, size0, **box)
+    assert got.shape == (X.shape[0], 2)
+    assert (got[:, 0] >= box["SIZE_lower"]).all() and (got[:, 0] <= box["SIZE_upper"]).all()
+    assert (got[:, 1] >= box["MU_lower"]).all() and (got[:, 1] <= box["MU_upper"]).all()
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+    live = (X > 0).sum(axis=1) > 0
+    assert np.array_equal(got[~live], want[~live])                       # all-zero genes: the projected start
+    assert (rel[live].max(axis=1) <= 1e-6).mean() >= 0.8, rel[live].max(axis=1)
+    # along the flat size-mu ridge of a sparse gene two equally good stopping points can sit percents apart:
+    # what has to agree everywhere is the likelihood they reach
+    lg = np.array([oracle.MarginalF_NB_2D(got[g], X[g], beta) for g in range(X.shape[0])])
+    lw = np.array([oracle.MarginalF_NB_2D(want[g], X[g], beta) for g in range(X.shape[0])])
+    done = (conv == 0) & (wconv == 0)                # genes whose spg converged (the others ran into maxfeval = 500)
+    assert done.mean() > 0.8
+    assert (np.abs(lg - lw)[done] <= 1e-8 * np.abs(lw[done]) + 1e-8).all(), np.abs(lg - lw)[done].max()
+    # a run cut off at 500 evaluations on a near-flat ridge (genes with one or two counts) stops wherever it is:
+    # the two walks still end at the same height to 1e-4
+    assert (np.abs(lg - lw) <= 1e-4 * np.abs(lw) + 1e-8).all(), np.abs(lg - lw).max()
+    assert rel.max() < 0.5, rel.max()
+    assert (conv == wconv).mean() >= 0.9
+    assert abs(nfe.sum() / (wcnt[:, 0] + wcnt[:, 1]).sum() - 1) < 0.05     # same amount of work
+    # the fitted point is at least as good as the start (and as the 1-D fit with mu fixed)
+    l0 = np.array([oracle.MarginalF_NB_2D([min(max(size0[g], box["SIZE_lower"]), box["SIZE_upper"]), mu0[g]], X[g], beta)
+                   for g in range(X.shape[0])])
+    assert (lg >= l0 - 1e-9 * np.abs(l0)).all()
+
+
+def test_fit_2d_analytic_gradient_and_prior_fun(bn, ctx, oracle, small):
+    """GR=TRUE (GradientFun_NB_2D) reaches the same optimum as the forward-difference run; Prior_fun(FIX_MU=FALSE)
+    returns the reference's structure: MME_prior, BB_prior (size, mu), MME_SIZE_adjust from BB_prior[, 1]."""
+    X, beta = small["X"][:60, :250], small["beta"][:250]
+    P = bn.Prior_fun(X, beta, FIX_MU=False, verbose=False, ctx=ctx, return_info=True)
+    Pg = bn.Prior_fun(X, beta, FIX_MU=False, GR=True, verbose=False, ctx=ctx)
+    assert set(P) >= {"MME_prior", "BB_prior", "MME_SIZE_adjust", "BETA_vec"} and set(P["BB_prior"]) == {"size", "mu"}
+    Po = oracle.Prior_fun(oracle.CSC.from_dense(X), beta, BB_SIZE=False)
+    np.testing.assert_allclose(P["MME_prior"]["MME_MU"], Po["MME_prior"]["MME_MU"], rtol=1e-13)
+    adj = oracle.AdjustSIZE_fun(P["BB_prior"]["size"], P["MME_prior"]["MME_MU"], P["MME_prior"]["MME_SIZE"])
+    np.testing.assert_allclose(P["MME_SIZE_adjust"], adj, rtol=1e-10)
+    info = P["_info"]
+    assert info["mu_lower"] == P["MME_prior"]["MME_MU"].min() and info["mu_upper"] == P["MME_prior"]["MME_MU"].max()
+    lf = np.array([oracle.MarginalF_NB_2D([P["BB_prior"]["size"][g], P["BB_prior"]["mu"][g]], X[g], beta) for g in range(60)])
+    lgr = np.array([oracle.MarginalF_NB_2D([Pg["BB_prior"]["size"][g], Pg["BB_prior"]["mu"][g]], X[g], beta) for g in range(60)])
+    conv_ok = (P["_info"]["conv"] == 0)
+    assert (np.abs(lf - lgr)[conv_ok] <= 1e-6 * np.abs(lf[conv_ok]) + 1e-6).all(), np.abs(lf - lgr)[conv_ok].max()
+    assert (np.abs(lf - lgr) <= 1e-4 * np.abs(lf) + 1e-3).all(), np.abs(lf - lgr).max()      # runs cut off at maxfeval
+    # device gradient against the oracle's GradientFun_NB_2D on one gene
+    g = int(np.argmax((X > 0).sum(axis=1)))
+    par = np.array([P["BB_prior"]["size"][g] * 1.3, P["BB_prior"]["mu"][g] * 0.8])
+    np.testing.assert_allclose(bn.GradientFun_NB_2D(par, X[g], beta, ctx=ctx), oracle.GradientFun_NB_2D(par, X[g], beta), rtol=1e-9)
