@@ -1,6 +1,6 @@
 /*
  * baynorm_b200_shim.c -- the R side of the drop-in boundary: a plain-C `.Call` shim that forwards
- * the reference's registered routines (src/RcppExports.cpp:211-228) and three new batched entries
+ * the reference's registered routines (src/RcppExports.cpp:211-228) and six new batched entries
  * to libbaynorm_b200.so.  NOT compiled or executed in this repository (no R toolchain in the
  * image); it is the binding a maintainer adds to the package's src/ directory.  Build:
  *     PKG_CPPFLAGS = -I<repo>/include        PKG_LIBS = -L<repo>/baynorm_b200 -lbaynorm_b200
@@ -240,6 +240,60 @@ SEXP bnb_prior(SEXP Data, SEXP BETA_vec, SEXP BB_SIZE, SEXP GR)
     return L;
 }
 
+/* BB_Fun(FIX_MU = FALSE): G x 2 matrix c('size', 'mu') of R/PRIOR_FUNCTIONS.R:457-470, :543-546 */
+SEXP bnb_fit_size_mu(SEXP Data, SEXP BETA_vec, SEXP mu0, SEXP size0, SEXP lower, SEXP upper, SEXP GR)
+{
+    bn_mat *m = upload(Data);
+    int64_t info[4];
+    bn_mat_info(m, info);
+    bn_fit_opts o;
+    bn_fit_opts_default(&o);
+    o.use_gradient = Rf_asLogical(GR) == TRUE;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, info[0], 2)); /* column 1 = size, column 2 = mu */
+    /* lower = c(SIZE_lower, MU_lower), upper = c(SIZE_upper, MU_upper) as in the parallel = TRUE branch (:414-419) */
+    int rc = bn_fit_size_mu(ctx(), m, REAL(BETA_vec), REAL(mu0), REAL(size0), REAL(lower)[0], REAL(upper)[0], REAL(lower)[1],
+                            REAL(upper)[1], &o, REAL(out), REAL(out) + info[0], NULL, NULL);
+    bn_mat_free(m);
+    check(rc);
+    UNPROTECT(1);
+    return out;
+}
+
+/* BetaFun (R/PRIOR_FUNCTIONS.R:30-71): list(BETA, selected) -- selected is a logical vector over the genes */
+SEXP bnb_beta_fun(SEXP Data, SEXP MeanBETA)
+{
+    bn_mat *m = upload(Data);
+    int64_t info[4];
+    bn_mat_info(m, info);
+    SEXP L = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(L, 0, Rf_allocVector(REALSXP, info[1]));
+    SET_VECTOR_ELT(L, 1, Rf_allocVector(LGLSXP, info[0]));
+    int rc = bn_beta_fun(ctx(), m, Rf_asReal(MeanBETA), REAL(VECTOR_ELT(L, 0)), (int32_t *)LOGICAL(VECTOR_ELT(L, 1)), NULL);
+    bn_mat_free(m);
+    check(rc);
+    UNPROTECT(1);
+    return L;
+}
+
+/* SyntheticControl (R/synthetic_controls.r:57-70): list(N_c, lambda) */
+SEXP bnb_synthetic_control(SEXP Data, SEXP BETA_vec)
+{
+    bn_mat *m = upload(Data);
+    int64_t info[4];
+    bn_mat_info(m, info);
+    GetRNGstate();
+    const uint64_t seed = ((uint64_t)(unif_rand() * 4294967296.0) << 32) | (uint64_t)(unif_rand() * 4294967296.0);
+    PutRNGstate();
+    SEXP L = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(L, 0, Rf_allocMatrix(REALSXP, info[0], info[1]));
+    SET_VECTOR_ELT(L, 1, Rf_allocVector(REALSXP, info[0]));
+    int rc = bn_synthetic_control(ctx(), m, REAL(BETA_vec), seed, REAL(VECTOR_ELT(L, 1)), REAL(VECTOR_ELT(L, 0)));
+    bn_mat_free(m);
+    check(rc);
+    UNPROTECT(1);
+    return L;
+}
+
 /* default BETA_vec of R/bayNorm.r:164-170 (+ the range check of :185-187) */
 SEXP bnb_beta_default(SEXP Data)
 {
@@ -272,6 +326,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"bnb_fit_size", (DL_FUNC)&bnb_fit_size, 7},
     {"bnb_prior", (DL_FUNC)&bnb_prior, 4},
     {"bnb_beta_default", (DL_FUNC)&bnb_beta_default, 1},
+    {"bnb_fit_size_mu", (DL_FUNC)&bnb_fit_size_mu, 7},
+    {"bnb_beta_fun", (DL_FUNC)&bnb_beta_fun, 2},
+    {"bnb_synthetic_control", (DL_FUNC)&bnb_synthetic_control, 2},
     {NULL, NULL, 0}};
 
 void R_init_bayNorm(DllInfo *dll)
