@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
             for (int64_t k = tid; k < g.nnz; k += TPG) {
                 const uint64_t e0 = __ldg(g.nz + k);
                 const double x = (double)(uint32_t)e0;
-                kk += x * (g.lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
+                kk += x * (g.lmu + __ldg(logbeta + (e0 >> 32))) - bn_lfact(x);
                 const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
                 if (xi > 0) atomicAdd(&hist[xi - 1], 1u); // an explicitly stored zero has no lgamma term
                 xm = max(xm, xi);
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(256, MINB)
             for (int64_t k = tid; k < sl.nnz; k += 256) {
                 const uint64_t e0 = __ldg(sl.nz + k);
                 const double x = (double)(uint32_t)e0;
-                kk += x * (lmu + __ldg(logbeta + (e0 >> 32))) - lgamma(x + 1.0);
+                kk += x * (lmu + __ldg(logbeta + (e0 >> 32))) - bn_lfact(x);
                 const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
                 if (xi > 0) atomicAdd(&sl.tail[xi - 1], 1u); // an explicitly stored zero has no lgamma term
                 xm = max(xm, xi);
@@ -1161,7 +1161,7 @@ __global__ void __launch_bounds__(256, 4)
             const uint64_t e0 = __ldg(g.nz + k);
             const double x = (double)(uint32_t)e0;
             if (x > 0.0) { // explicit zeros carry no term
-                k0 += x * __ldg(logbeta + (e0 >> 32)) - lgamma(x + 1.0);
+                k0 += x * __ldg(logbeta + (e0 >> 32)) - bn_lfact(x);
                 xs += x;
                 const int xi = x > (double)HMAX ? HMAX + 1 : (int)x;
                 atomicAdd(&hist[xi - 1], 1u);

@@ -103,6 +103,16 @@ __device__ __forceinline__ double bn_log1p_small(double y)
     return fma(y * y, p, y);
 }
 
+// log(k!) for the integer counts of the likelihood constant sum_j lgamma(x_j + 1): a 2 KB table (L1-resident)
+// up to 256, libdevice beyond
+__device__ const double g_bn_lfact[257] = {
+#include "bn_lfact_table.inc"
+};
+__device__ __forceinline__ double bn_lfact(double x)
+{
+    return x <= 256.0 ? __ldg(g_bn_lfact + (int)x) : lgamma(x + 1.0);
+}
+
 // lgamma(z) for z >= 64 by Stirling's series through 1/(1260 z^5) (next term 1/(1680 z^7) < 4e-16)
 __device__ __forceinline__ double bn_lgamma_stirling(double z, const BnLogEntry *__restrict__ tab)
 {
