@@ -43,7 +43,13 @@ struct bn_mat {
     // general real-valued matrices (EstPrior on already normalised data): separate arrays
     int32_t *cell = nullptr;   // [nnz]
     double *rval = nullptr;    // [nnz]
+    // blocked column pointers (built on demand by bn_mat_ensure_blockptr): blockptr[t * C + j] = first position of
+    // column j whose row is >= t * BN_ROWBLOCK, t = 0 .. nblock (row nblock = colptr[j + 1]).  The posterior
+    // kernels give every warp one row block: its slice of a column is [blockptr[t][j], blockptr[t + 1][j]).
+    uint32_t *blockptr = nullptr; // [(nblock + 1) * C]
+    int64_t nblock = 0;
 };
+#define BN_ROWBLOCK 128
 
 // ---------------------------------------------------------------------------------
 // error helpers
@@ -174,6 +180,7 @@ template <typename T> struct DevOut {
 
 int bn_sync(bn_ctx *ctx);
 int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m);
+int bn_mat_ensure_blockptr(bn_ctx *ctx, const bn_mat *m);
 // in-place all-reduce over shards through the user hook (no-op when world == 1)
 int bn_allreduce(bn_ctx *ctx, double *dev, int64_t count, int op);
 
