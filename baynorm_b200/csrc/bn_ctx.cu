@@ -77,6 +77,8 @@ void bn_ctx_destroy(bn_ctx *ctx)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (void *p : ctx->scratch)
+        if (p) cudaFree(p);
     delete ctx;
 }
 
@@ -107,6 +109,24 @@ int bn_ctx_set_allreduce(bn_ctx *ctx, bn_allreduce_fn fn, void *user, int rank, 
 }
 
 } // extern "C"
+
+int bn_ctx_scratch(bn_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            BN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            BN_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        const size_t want = bytes + bytes / 8; // headroom: column blocks of slightly different width re-use it
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) return bn_fail(ctx, BN_ERR_OOM, "scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return BN_OK;
+}
 
 int bn_sync(bn_ctx *ctx)
 {
@@ -358,19 +378,7 @@ extern "C" int bn_mat_info(const bn_mat *m, int64_t out[4])
 extern "C" int bn_mat_drop_gene_major(bn_mat *m)
 {
     if (!m) return BN_ERR_INVALID;
-    if (m->has_csr) {
-        cudaSetDevice(m->ctx->device);
-        cudaStream_t st = m->ctx->stream;
-        if (m->rowptr) cudaFreeAsync(m->rowptr, st);
-        if (m->gm) cudaFreeAsync(m->gm, st);
-        if (m->cell) cudaFreeAsync(m->cell, st);
-        if (m->rval) cudaFreeAsync(m->rval, st);
-        m->gm = nullptr;
-        m->rowptr = nullptr;
-        m->cell = nullptr;
-        m->rval = nullptr;
-        m->has_csr = false;
-    }
+    m->has_csr = false; // the buffers stay with the matrix: the rebuild overwrites them in place
     return BN_OK;
 }
 
@@ -641,32 +649,32 @@ int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
     cudaSetDevice(ctx->device);
     const int64_t nnz = m->nnz, G = m->G;
     if (nnz > 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz > 2^31-1 per shard in the gene-major build");
-    BN_CUDA(ctx, cudaMallocAsync((void **)&m->rowptr, (size_t)(G + 1) * 8, ctx->stream));
+    if (!m->rowptr) BN_CUDA(ctx, cudaMallocAsync((void **)&m->rowptr, (size_t)(G + 1) * 8, ctx->stream));
     int bits = 1;
     while ((1LL << bits) < G) bits++;
     if (m->is_count) {
         // stable sort of (row -> packed (cell, count)) pairs: the sorted values ARE the gene-major matrix
-        BN_CUDA(ctx, cudaMallocAsync((void **)&m->gm, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
+        if (!m->gm) BN_CUDA(ctx, cudaMallocAsync((void **)&m->gm, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
         if (nnz) {
-            DevBuf<uint64_t> packed;
-            DevBuf<int32_t> kout;
-            BN_TRY(packed.alloc(ctx, (size_t)nnz));
-            BN_TRY(kout.alloc(ctx, (size_t)nnz));
+            struct { uint64_t *p; } packed;
+            struct { int32_t *p; } kout;
+            BN_TRY(bn_ctx_scratch(ctx, 2, (size_t)nnz * 8, (void **)&packed.p));
+            BN_TRY(bn_ctx_scratch(ctx, 3, (size_t)nnz * 4, (void **)&kout.p));
             const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
             BN_LAUNCH(ctx, k_pack_nz, blocks, 256, 0, m->C, m->colptr, m->val, packed.p);
             size_t tb = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tb, (const int32_t *)m->rowidx, kout.p, (const uint64_t *)packed.p, m->gm,
                                             (int)nnz, 0, bits, ctx->stream);
-            DevBuf<char> tmp;
-            BN_TRY(tmp.alloc(ctx, tb));
+            struct { char *p; } tmp;
+            BN_TRY(bn_ctx_scratch(ctx, 4, tb, (void **)&tmp.p));
             BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p,
                                                          (const uint64_t *)packed.p, m->gm, (int)nnz, 0, bits, ctx->stream));
             ctx->launches += (bits + 7) / 8 + 1;
             BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)((nnz + 255) / 256), 256, 0, kout.p, nnz, G, m->rowptr);
         }
     } else {
-        BN_CUDA(ctx, cudaMallocAsync((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
-        BN_CUDA(ctx, cudaMallocAsync((void **)&m->rval, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
+        if (!m->cell) BN_CUDA(ctx, cudaMallocAsync((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
+        if (!m->rval) BN_CUDA(ctx, cudaMallocAsync((void **)&m->rval, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
         if (nnz) {
             DevBuf<int32_t> kout;
             DevBuf<uint32_t> v0, v1;

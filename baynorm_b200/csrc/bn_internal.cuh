@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -23,7 +25,14 @@ struct bn_ctx {
     int rank = 0, world = 1;
     cudaEvent_t ev[8] = {};
     double *pinned = nullptr; // 64 doubles of page-locked host memory for truly asynchronous scalar read-backs
+    // grow-only device scratch kept across calls (slots 0-1: the 3-D sampler's element lists; 2-4: pack / key /
+    // sort buffers of the gene-major build): re-allocating GB-sized buffers per call through the stream-ordered
+    // pool was measured to stall the host for 5-400 ms every few calls
+    void *scratch[8] = {};
+    size_t scratch_bytes[8] = {};
 };
+// returns ctx->scratch[slot] with at least `bytes` bytes (contents undefined)
+int bn_ctx_scratch(bn_ctx *ctx, int slot, size_t bytes, void **out);
 
 struct bn_mat {
     bn_ctx *ctx = nullptr;
@@ -111,7 +120,15 @@ template <typename T> struct DevBuf {
         ctx = c;
         n = count;
         if (count == 0) count = 1;
+        static const bool trace = getenv("BN_TRACE_ALLOC") != nullptr;
+        struct timespec t0_, t1_;
+        if (trace) clock_gettime(CLOCK_MONOTONIC, &t0_);
         cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), c->stream);
+        if (trace) {
+            clock_gettime(CLOCK_MONOTONIC, &t1_);
+            const double ms = (t1_.tv_sec - t0_.tv_sec) * 1e3 + (t1_.tv_nsec - t0_.tv_nsec) * 1e-6;
+            if (ms > 0.5) fprintf(stderr, "[bn alloc] %.1f ms for %zu bytes\n", ms, count * sizeof(T));
+        }
         if (e != cudaSuccess) {
             p = nullptr;
             return bn_fail(c, BN_ERR_OOM, "device allocation of %zu bytes failed: %s", count * sizeof(T),

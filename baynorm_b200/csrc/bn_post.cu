@@ -837,10 +837,10 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
             const size_t max_ctas = (size_t)std::max<int64_t>(ctas64, std::min<int64_t>(ctas4, (int64_t)sms * 128 + tiles_s));
             const size_t cap = (((size_t)(per_elem * (double)m->G * (double)chunk) + SW_HBLOCK - 1) / SW_HBLOCK + (size_t)SW_WARPS * max_ctas) * SW_HBLOCK; // whole blocks
             if (cap > 0xfffffff0u) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: element list too long");
-            DevBuf<HeavyItem> hl, fl;
+            struct { HeavyItem *p; } hl, fl; // context scratch: kept across calls (see bn_ctx_scratch)
             DevBuf<unsigned int> hc; // per chunk: {list slots, fallback entries, -, table-kernel cursor}; hc[2] = max slots over the chunks
-            BN_TRY(hl.alloc(ctx, cap));
-            BN_TRY(fl.alloc(ctx, cap));
+            BN_TRY(bn_ctx_scratch(ctx, 0, cap * sizeof(HeavyItem), (void **)&hl.p));
+            BN_TRY(bn_ctx_scratch(ctx, 1, cap * sizeof(HeavyItem), (void **)&fl.p));
             BN_TRY(hc.alloc(ctx, 4));
             BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 4 * sizeof(unsigned int), ctx->stream));
             for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
