@@ -570,9 +570,8 @@ __global__ void k_iota_u32(uint32_t *__restrict__ v, int64_t n)
 __global__ void __launch_bounds__(256) k_rowptr_from_sorted(const int32_t *__restrict__ key, int64_t nnz, int64_t G,
                                                             int64_t *__restrict__ rowptr)
 {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < nnz) {
-        const int32_t cur = key[k], prev = k > 0 ? key[k - 1] : -1;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += gridDim.x * (int64_t)blockDim.x) {
+        const int32_t cur = __ldg(key + k), prev = k > 0 ? __ldg(key + k - 1) : -1;
         for (int32_t r = prev + 1; r <= cur; r++) rowptr[r] = k;
         if (k == nnz - 1)
             for (int64_t r = (int64_t)cur + 1; r <= G; r++) rowptr[r] = nnz;
@@ -670,7 +669,7 @@ int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
             BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p,
                                                          (const uint64_t *)packed.p, m->gm, (int)nnz, 0, bits, ctx->stream));
             ctx->launches += (bits + 7) / 8 + 1;
-            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)((nnz + 255) / 256), 256, 0, kout.p, nnz, G, m->rowptr);
+            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)std::min<int64_t>((nnz + 255) / 256, 148 * 32), 256, 0, kout.p, nnz, G, m->rowptr);
         }
     } else {
         if (!m->cell) BN_CUDA(ctx, cudaMallocAsync((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
@@ -690,7 +689,7 @@ int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
             BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p, (const uint32_t *)v0.p,
                                                          v1.p, (int)nnz, 0, bits, ctx->stream));
             ctx->launches += (bits + 7) / 8 + 1;
-            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)((nnz + 255) / 256), 256, 0, kout.p, nnz, G, m->rowptr);
+            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)std::min<int64_t>((nnz + 255) / 256, 148 * 32), 256, 0, kout.p, nnz, G, m->rowptr);
             BN_LAUNCH(ctx, k_csr_gather, 148 * 8, 256, 0, nnz, m->C, v1.p, m->colptr, m->val, m->cell, m->rval);
         }
     }

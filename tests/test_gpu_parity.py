@@ -693,6 +693,41 @@ def test_ragged_shapes_and_empty_columns(bn, ctx, oracle):
         bn.Prior_fun(bn.Check_input(np.ones((3, 1)), ctx), np.array([0.1]), verbose=False)   # MME needs >= 2 cells
 
 
+def test_explicitly_stored_zeros(bn, ctx, oracle, small):
+    """A dgCMatrix may carry explicitly stored zeros (e.g. after `x[x == 1] <- 0`).  They are zeros for every
+    stage: BETA, MME, the fit (no lgamma term, no tail-table entry), the posterior and BetaFun's zero fraction."""
+    import scipy.sparse as sp
+    X = small["X"][:90, :260].copy()
+    beta = small["beta"][:260]
+    keep = X.copy()
+    keep[keep == 1] = 0.0                                      # the values the explicit zeros stand for
+    S = sp.csc_matrix(X)
+    S.data[S.data == 1] = 0.0                                  # same pattern, zeros stored
+    assert (S.data == 0).sum() > 100
+    Mz = bn.Check_input(S, ctx)
+    Mk = bn.Check_input(keep, ctx)
+    assert Mz.nnz > Mk.nnz
+    Pz = bn.Prior_fun(Mz, beta, verbose=False)
+    Pk = bn.Prior_fun(Mk, beta, verbose=False)
+    for a, b in ((Pz["MME_prior"]["MME_MU"], Pk["MME_prior"]["MME_MU"]), (Pz["MME_prior"]["MME_SIZE"], Pk["MME_prior"]["MME_SIZE"])):
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+    assert (rel_err(Pz["BB_prior"]["BB_SIZE"], Pk["BB_prior"]["BB_SIZE"]) <= 1e-6).mean() >= 0.9
+    np.testing.assert_allclose(Pz["MME_SIZE_adjust"], Pk["MME_SIZE_adjust"], rtol=1e-5)
+    size, mu = Pk["MME_SIZE_adjust"], Pk["MME_prior"]["MME_MU"]
+    assert np.array_equal(bn.Main_mode_NB_Bay(Mz, beta, size, mu), bn.Main_mode_NB_Bay(Mk, beta, size, mu))
+    assert np.array_equal(bn.Main_mean_NB_Bay(Mz, beta, size, mu), bn.Main_mean_NB_Bay(Mk, beta, size, mu))
+    assert np.array_equal(bn.Main_NB_Bay(Mz, beta, size, mu, S=4, seed=3), bn.Main_NB_Bay(Mk, beta, size, mu, S=4, seed=3))
+    bz, bk = bn.BetaFun(Mz, 0.06, ctx=ctx, with_stats=True), bn.BetaFun(Mk, 0.06, ctx=ctx, with_stats=True)
+    assert np.array_equal(bz["stats"]["dropout"], bk["stats"]["dropout"])
+    f2z = bn.BB_Fun(Mz, beta, mu, Pk["MME_prior"]["MME_SIZE"], FIX_MU=False, SIZE_lower=0.01, SIZE_upper=10, MU_lower=0.0,
+                    MU_upper=float(mu.max()), ctx=ctx)
+    f2k = bn.BB_Fun(Mk, beta, mu, Pk["MME_prior"]["MME_SIZE"], FIX_MU=False, SIZE_lower=0.01, SIZE_upper=10, MU_lower=0.0,
+                    MU_upper=float(mu.max()), ctx=ctx)
+    lz = np.array([oracle.MarginalF_NB_2D(f2z[g], keep[g], beta) for g in range(90)])
+    lk = np.array([oracle.MarginalF_NB_2D(f2k[g], keep[g], beta) for g in range(90)])
+    assert (np.abs(lz - lk) <= 1e-4 * np.abs(lk) + 1e-6).all()
+
+
 def test_posterior_on_non_integer_data(bn, ctx, oracle, small):
     """The posterior closed forms accept any non-negative doubles (e.g. UMI_sffl-scaled data)."""
     X = small["X"][:50, :40] * 0.37
