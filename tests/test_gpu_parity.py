@@ -829,20 +829,30 @@ def test_synthetic_control(bn, ctx, oracle, small):
 
 
 # ------------------------------------------------------------------------ BetaFun
-@pytest.mark.parametrize("which", ["fixture", "dense_even", "dense_odd"])
+@pytest.mark.parametrize("which", ["fixture", "dense_even", "dense_odd", "clamp"])
 def test_beta_fun(bn, ctx, oracle, fixture_data, which):
     """R/PRIOR_FUNCTIONS.R:30-71 against the dense numpy restatement: zero fractions, the order statistics of
     the genes that can be selected, the selected set and BETA."""
+    mean_beta = 0.06
     if which == "fixture":
         X = fixture_data["inputdata"]                                # 20 x 74, the reference's own example call
+    elif which == "clamp":                                           # BETA >= 1 and BETA <= 0 both occur before clamping
+        rng = np.random.default_rng(8)
+        depth = np.ones(30)
+        depth[0], depth[1] = 40.0, 0.01
+        X = rng.poisson(6.0 * depth[None, :] * rng.uniform(0.5, 2.0, (40, 1))).astype(np.float64)
+        X[39, :] = 0.0
+        X[39, 1] = 3.0
+        X[:39, 1] = 0.0
+        mean_beta = 0.5
     else:
         rng = np.random.default_rng(21)
         G, Cn = 260, (150 if which == "dense_even" else 151)
         mu = rng.lognormal(1.5, 1.2, G)
         X = rng.poisson(rng.gamma(2.0, mu[:, None] / 2.0, (G, Cn)) * rng.uniform(0.5, 1.5, Cn)[None, :]).astype(np.float64)
         X[:, X.sum(axis=0) == 0] += 1.0
-    got = bn.BetaFun(X, 0.06, ctx=ctx, with_stats=True)
-    ref = oracle.BetaFun(X, 0.06)
+    got = bn.BetaFun(X, mean_beta, ctx=ctx, with_stats=True)
+    ref = oracle.BetaFun(X, mean_beta)
     np.testing.assert_allclose(got["stats"]["dropout"], ref["stats"]["dropout"], rtol=0, atol=0)
     cand = ref["stats"]["dropout"] < 0.35
     assert cand.sum() > 3, "test matrix has no candidate genes"
@@ -853,7 +863,8 @@ def test_beta_fun(bn, ctx, oracle, fixture_data, which):
     assert 0 < len(ref["Selected_genes"]) < X.shape[0]
     np.testing.assert_allclose(got["BETA"], ref["BETA"], rtol=1e-12)
     assert (got["BETA"] > 0).all() and (got["BETA"] < 1).all()
-    assert abs(got["BETA"].mean() - 0.06) < 1e-12 or (ref["BETA"] != ref["BETA"].clip(0, 1)).any()
+    if which != "clamp":
+        assert abs(got["BETA"].mean() - mean_beta) < 1e-12
 
 
 # ------------------------------------------------------------------------ FIX_MU = FALSE

@@ -166,3 +166,84 @@ def test_conditions_orchestration(oracle):
     assert np.array_equal(solo["Bay_out"], r["Bay_out_list"]["Group 1"])
     g = oracle.bayNorm(M, BETA_vec=beta, Conditions=cond, Prior_type="GG", mean_version=True)
     assert g["PRIORS_LIST"]["Group 1"] is g["PRIORS_LIST"]["Group 2"]
+
+
+def test_betafun_restatement(oracle, fixture_data):
+    """BetaFun (R/PRIOR_FUNCTIONS.R:30-71) restated: order statistics against an element-by-element pure-Python
+    median / mad (R's definitions: mean of the two middle values for even n, constant 1.4826), the selection rule
+    and the clamping order of BETA on the bundled example (the reference's own `BetaFun(inputdata, 0.06)` call)."""
+    A = fixture_data["inputdata"]
+    r = oracle.BetaFun(A, 0.06)
+    xx = A.sum(axis=0)
+    for g in (0, 3, 7, 19):
+        v = sorted(float(np.log(A[g, j] / xx[j] * xx.mean() + 1.0)) for j in range(A.shape[1]))
+        n = len(v)
+        med = v[n // 2] if n % 2 else (v[n // 2 - 1] + v[n // 2]) / 2
+        dev = sorted(abs(t - med) for t in v)
+        mad = 1.4826 * (dev[n // 2] if n % 2 else (dev[n // 2 - 1] + dev[n // 2]) / 2)
+        assert abs(r["stats"]["median"][g] - med) < 1e-15 and abs(r["stats"]["mad"][g] - mad) < 1e-15
+        assert r["stats"]["max"][g] == v[-1]
+        assert r["stats"]["dropout"][g] == float((A[g] == 0).sum()) / n
+    sel = r["Selected_genes"]
+    assert len(sel) == 10 and set(sel) <= set(np.nonzero(r["stats"]["dropout"] < 0.35)[0])
+    t = A[sel].sum(axis=0)
+    np.testing.assert_allclose(r["BETA"], t / t.mean() * 0.06, rtol=1e-15)       # nothing to clamp on the example
+    assert abs(r["BETA"].mean() - 0.06) < 1e-15 and r["BETA"].min() > 0 and r["BETA"].max() < 1
+    # clamping order (:61-66): >= 1 -> largest value below 1 first, then <= 0 -> smallest positive value
+    rng = np.random.default_rng(8)
+    depth = np.ones(30)
+    depth[0], depth[1] = 40.0, 0.01                       # one huge library, one nearly empty cell
+    B = rng.poisson(6.0 * depth[None, :] * rng.uniform(0.5, 2.0, (40, 1))).astype(float)
+    B[39, :] = 0.0
+    B[39, 1] = 3.0                                        # a high-dropout gene keeps the empty cell's column sum positive
+    B[:39, 1] = 0.0
+    r2 = oracle.BetaFun(B, 0.5)
+    sel2 = r2["Selected_genes"]
+    assert len(sel2) > 5 and 39 not in sel2
+    t2 = B[sel2].sum(axis=0)
+    raw = t2 / t2.mean() * 0.5
+    assert (raw >= 1).any() and (raw <= 0).any()
+    want = raw.copy()
+    want[want >= 1] = want[want < 1].max()
+    want[want <= 0] = want[want > 0].min()
+    assert np.array_equal(r2["BETA"], want) and (want > 0).all() and (want < 1).all()
+
+
+def test_synthetic_control_restatement(oracle, fixture_data):
+    """SyntheticControl (R/synthetic_controls.r:57-70): lambda against the formula written out per gene, and the
+    law of the thinned Poisson counts."""
+    A, beta = fixture_data["inputdata"], fixture_data["inputbeta"]
+    r = oracle.SyntheticControl(A, beta, seed=3)
+    cs = A.sum(axis=0)
+    depth = np.mean(cs / beta)
+    for g in (0, 5, 19):
+        assert abs(r["lambda"][g] - np.mean(A[g] / cs * depth)) < 1e-12 * r["lambda"][g]
+    big = oracle.SyntheticControl(np.tile(A, (1, 40)), np.tile(beta, 40), seed=4)
+    lam = big["lambda"][:, None] * np.tile(beta, 40)[None, :]
+    z = (big["N_c"].sum(axis=1) - lam.sum(axis=1)) / np.sqrt(lam.sum(axis=1))
+    assert np.abs(z).max() < 4.5
+
+
+def test_spg_2d_restatement(oracle, fixture_data):
+    """The 2-D spg (FIX_MU=FALSE, R/PRIOR_FUNCTIONS.R:457-470): with the mu box collapsed onto the start it is the
+    1-D fit; with the reference's box it never ends below the 1-D optimum and sits on a stationary point or a
+    bound of the restated likelihood."""
+    A, beta = fixture_data["inputdata"], fixture_data["inputbeta"]
+    M = oracle.CSC.from_dense(A)
+    pri = oracle.EstPrior(M, beta)
+    size0 = pri["SIZE"].copy()
+    size0[np.isnan(size0)] = np.nanmin(size0)
+    mu0 = pri["MU"]
+    lo, hi = float(size0.min()), float(np.ceil(size0.max()))
+    for g in (0, 4, 11):
+        p1, rc1, _ = oracle.spg_gene_1d(size0[g], mu0[g], A[g], beta, lo, hi)
+        p2, rc2, _ = oracle.spg_gene_2d([size0[g], mu0[g]], A[g], beta, [lo, mu0[g]], [hi, mu0[g]])
+        assert rc1 == rc2 and abs(p2[0] - p1) <= 1e-6 * p1 and p2[1] == mu0[g]
+        pf, rcf, _ = oracle.spg_gene_2d([size0[g], mu0[g]], A[g], beta, [lo, mu0.min()], [hi, mu0.max()])
+        l1 = oracle.MarginalF_NB_1D(p1, mu0[g], A[g], beta)
+        lf = oracle.MarginalF_NB_2D(pf, A[g], beta)
+        assert lf >= l1 - 1e-7 * abs(l1)
+        gr = oracle.GradientFun_NB_2D(pf, A[g], beta)
+        for i, (l, h) in enumerate(((lo, hi), (mu0.min(), mu0.max()))):
+            on_bound = abs(pf[i] - l) < 1e-9 or abs(pf[i] - h) < 1e-9
+            assert on_bound or abs(gr[i]) < 5e-3 * max(1.0, abs(lf)), (g, i, pf, gr)
