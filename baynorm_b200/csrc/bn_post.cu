@@ -209,8 +209,10 @@ __global__ void __launch_bounds__(PW_WARPS * 32, MINB)
     double *xt = s_x[warp];
     // slice bounds of columns lane and lane + 32 from the blocked column pointers (the warp's genes are EPL / 4
     // row blocks), and their BETA
-    const uint32_t *bp_lo = blockptr + (w0 / BN_ROWBLOCK) * Ctot + col0 + jb;
-    const uint32_t *bp_hi = bp_lo + (PW_GENES / BN_ROWBLOCK) * Ctot;
+    const int64_t nblock = (G + BN_ROWBLOCK - 1) / BN_ROWBLOCK, blk_lo = w0 / BN_ROWBLOCK;
+    const int64_t blk_hi = blk_lo + PW_GENES / BN_ROWBLOCK < nblock ? blk_lo + PW_GENES / BN_ROWBLOCK : nblock; // row nblock = column end
+    const uint32_t *bp_lo = blockptr + blk_lo * Ctot + col0 + jb;
+    const uint32_t *bp_hi = blockptr + blk_hi * Ctot + col0 + jb;
     uint32_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
     double beta_a = 0.0, beta_b = 0.0;
     if (lane < nc) {
@@ -895,11 +897,15 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         if (epl == 4) BN_LAUNCH(ctx, (k_posterior_w<MODE_, PF_, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS); \
         else BN_LAUNCH(ctx, (k_posterior_w<MODE_, PF_, 3, 8>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);          \
     } while (0)
+        static int pfd = 0; // slices prefetched per column for >= 20 % dense matrices: 3 x 32 (default) or 5 x 32 non-zeros
+        if (!pfd) pfd = (getenv("BN_POST_PFD") && atoi(getenv("BN_POST_PFD")) == 5) ? 5 : 3;
         if (mode == POST_MEAN) {
-            if (densew) POSTW_GO(POST_MEAN, 5);
+            if (densew && pfd == 5) POSTW_GO(POST_MEAN, 5);
+            else if (densew) POSTW_GO(POST_MEAN, 3);
             else POSTW_GO(POST_MEAN, 1);
         } else {
-            if (densew) POSTW_GO(POST_MODE, 5);
+            if (densew && pfd == 5) POSTW_GO(POST_MODE, 5);
+            else if (densew) POSTW_GO(POST_MODE, 3);
             else POSTW_GO(POST_MODE, 1);
         }
 #undef POSTW_GO
