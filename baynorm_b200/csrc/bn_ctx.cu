@@ -605,7 +605,15 @@ __global__ void __launch_bounds__(256) k_pack_nz(int64_t C, const int64_t *__res
     for (int64_t j = warp; j < C; j += nwarp) {
         const int64_t a = colptr[j], b = colptr[j + 1];
         const uint64_t hi = (uint64_t)j << 32;
-        for (int64_t k = a + lane; k < b; k += 32) packed[k] = hi | (uint64_t)(uint32_t)__ldcs(val + k);
+        int64_t k = a + lane;
+        for (; k + 96 < b; k += 128) { // four loads in flight per lane
+            const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + 32), v2 = __ldcs(val + k + 64), v3 = __ldcs(val + k + 96);
+            packed[k] = hi | (uint64_t)(uint32_t)v0;
+            packed[k + 32] = hi | (uint64_t)(uint32_t)v1;
+            packed[k + 64] = hi | (uint64_t)(uint32_t)v2;
+            packed[k + 96] = hi | (uint64_t)(uint32_t)v3;
+        }
+        for (; k < b; k += 32) packed[k] = hi | (uint64_t)(uint32_t)__ldcs(val + k);
     }
 }
 
