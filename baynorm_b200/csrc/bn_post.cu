@@ -971,23 +971,123 @@ extern "C" int bn_post_sample(bn_ctx *ctx, const bn_mat *m, const double *BETA_v
 }
 
 // ---------------------------------------------------------------------------------
-// DownSampling: dense column-major in/out, one binomial draw per element, 16 B/element.
+// DownSampling (src/bayNorm_main.cpp:892-915): dense column-major in/out, out[i,j] ~ Binomial(Data[i,j], beta_j),
+// 16 B/element of HBM traffic.  Four genes of a cell share ONE Philox block -- counter (gene / 4, cell), word =
+// gene % 4 -- so a draw is a pure function of (seed, gene, cell) and costs a quarter of a block; zeros cost nothing.
+// Counts with n min(p, 1-p) < 30 are inverted from 0 in float; larger ones (and counts beyond float's integer grid)
+// are listed and drawn by k_downsample_big with the FP64 BTRS path of bn_rbinom on a sub-stream of their own.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_downsample(int64_t G, int64_t C, const double *__restrict__ in,
-                                                    const double *__restrict__ beta, uint64_t seed,
-                                                    double *__restrict__ out)
+// the float path: sequential inversion from 0 with p <= 1/2:  f(0) = (1-p)^n,  f(k) = f(k-1) s (n-k+1)/k,  s = p/(1-p)
+__device__ __forceinline__ double ds_draw_small(double n, float pf, float L, float sratio, bool flip, uint32_t w)
 {
-    const int64_t total = G * C;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += gridDim.x * (int64_t)blockDim.x) {
-        const double n = __ldcs(in + e);
-        double r = 0.0;
-        if (n > 0.0) {
-            const int64_t j = e / G, i = e - j * G;
-            Philox g;
-            g.init(seed, (uint64_t)i + (uint64_t)j * 0x100000000ULL, 0x44533031u /* "DS01" */);
-            r = bn_rbinom(g, n, __ldg(beta + j));
+    const float nf = (float)n;
+    float f = __expf(nf * L), u = bn_u01f(w), k = 0.0f;
+    while (u > f && k < nf) {
+        u -= f;
+        k += 1.0f;
+        f *= sratio * __fdividef(nf - k + 1.0f, k);
+    }
+    return flip ? n - (double)k : (double)k;
+}
+__device__ __forceinline__ bool ds_is_big(double n, float pf) { return (float)n * pf >= 30.0f || n >= 16777216.0; }
+
+// A warp owns 32-gene x 32-cell tiles.  Loads and stores run with lane = gene (every instruction 256 contiguous
+// bytes); the draws run with lane = CELL through a padded shared-memory tile, one gene at a time, so the 32 lanes of a
+// draw instruction hold counts of the same gene (same scale -> similar inversion lengths) and each lane keeps its
+// column's p, log1p(-p) and p/q for the whole tile.  Measured against lane = gene for the draws: 15 -> 2x active
+// lanes per instruction.
+#define DS_WARPS 8
+__global__ void __launch_bounds__(DS_WARPS * 32, 3)
+    k_downsample(int64_t G, int64_t C, const double *__restrict__ in, const double *__restrict__ beta,
+                 const __grid_constant__ PhiloxKeys keys, double *__restrict__ out, int64_t *__restrict__ biglist,
+                 unsigned long long *__restrict__ bigcount)
+{
+    extern __shared__ double s_t[]; // [warp][cell][gene], rows padded to 33
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *T = s_t + wib * (32 * 33);
+    const int64_t tg = (G + 31) / 32, tc = (C + 31) / 32, total = tg * tc;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    for (int64_t t = warp; t < total; t += nwarp) {
+        const int64_t ct = t / tg, gt = t - ct * tg;
+        const int64_t g0 = gt * 32, c0 = ct * 32;
+        const int ncell = (int)(C - c0 < 32 ? C - c0 : 32);
+        const bool gin = g0 + lane < G;
+        // load: lane = gene
+#pragma unroll 8
+        for (int cc = 0; cc < 32; cc++) T[cc * 33 + lane] = (gin && cc < ncell) ? __ldcs(in + (c0 + cc) * G + g0 + lane) : 0.0;
+        __syncwarp();
+        // draw: lane = cell
+        const int64_t j = c0 + lane;
+        const double pp = (lane < ncell) ? __ldg(beta + j) : 0.0;
+        const bool flip = pp > 0.5;
+        const float pf = (float)(flip ? 1.0 - pp : pp);
+        const float L = log1pf(-pf), sratio = pf / (1.0f - pf);
+        for (int gi = 0; gi < 32; gi += 4) {
+            double n[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) n[q] = T[lane * 33 + gi + q];
+            double r[4] = {0.0, 0.0, 0.0, 0.0};
+            int nbig = 0;
+            if ((n[0] > 0.0 || n[1] > 0.0 || n[2] > 0.0 || n[3] > 0.0) && pp > 0.0) {
+                if (pp >= 1.0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) r[q] = n[q];
+                } else {
+                    uint32_t wd[4]; // one Philox block per (4 genes, cell): counter (gene / 4, cell), word = gene % 4
+                    const uint64_t gq = (uint64_t)(g0 + gi) >> 2;
+                    bn_philox_block(keys, (uint32_t)gq, (uint32_t)(gq >> 32), (uint32_t)j, (uint32_t)((uint64_t)j >> 32), wd[0], wd[1], wd[2],
+                                    wd[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (!(n[q] > 0.0)) continue;
+                        if (ds_is_big(n[q], pf)) nbig++; // drawn by k_downsample_big: BTRS never shares a warp with the inversion
+                        else r[q] = ds_draw_small(n[q], pf, L, sratio, flip, wd[q]);
+                    }
+                }
+            }
+            // warp-aggregated append of the big elements (element index = i + G j)
+            const unsigned any = __ballot_sync(0xffffffffu, nbig > 0);
+            if (any) {
+                int pre = nbig;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                    if (lane >= o) pre += v;
+                }
+                unsigned long long base = 0;
+                if (lane == 31) base = atomicAdd(bigcount, (unsigned long long)pre);
+                base = __shfl_sync(0xffffffffu, base, 31) + (unsigned long long)(pre - nbig);
+                if (nbig > 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (n[q] > 0.0 && ds_is_big(n[q], pf)) biglist[base++] = j * G + g0 + gi + q;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) T[lane * 33 + gi + q] = r[q];
         }
-        __stcs(out + e, r);
+        __syncwarp();
+        // store: lane = gene
+        if (gin) {
+#pragma unroll 8
+            for (int cc = 0; cc < 32; cc++)
+                if (cc < ncell) __stcs(out + (c0 + cc) * G + g0 + lane, T[cc * 33 + lane]);
+        }
+        __syncwarp();
+    }
+}
+
+// counts with n min(p, 1-p) >= 30 (or beyond float's integer grid): Hoermann's BTRS in FP64, one element per thread
+__global__ void __launch_bounds__(256) k_downsample_big(int64_t G, const double *__restrict__ in, const double *__restrict__ beta,
+                                                        uint64_t seed, const int64_t *__restrict__ biglist,
+                                                        const unsigned long long *__restrict__ bigcount, double *__restrict__ out)
+{
+    const int64_t n = (int64_t)*bigcount;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += gridDim.x * (int64_t)blockDim.x) {
+        const int64_t e = biglist[t], j = e / G, i = e - j * G;
+        Philox g;
+        g.init(seed, (uint64_t)i + (uint64_t)j * 0x100000000ULL, 0x44533032u /* "DS02" */);
+        out[e] = bn_rbinom(g, in[e], __ldg(beta + j));
     }
 }
 
@@ -1002,9 +1102,18 @@ extern "C" int bn_downsample(bn_ctx *ctx, int64_t G, int64_t C, const double *Da
     BN_TRY(b.bind(ctx, BETA_vec, (size_t)C));
     DevOut<double> o;
     BN_TRY(o.bind(ctx, out, (size_t)G * C));
-    const int64_t want = (G * C + 255) / 256;
-    const int grid = (int)std::min<int64_t>(want, 148 * 32);
-    BN_LAUNCH(ctx, k_downsample, grid, 256, 0, G, C, a.p, b.p, seed, o.p);
+    const int64_t want = (((G + 31) / 32) * ((C + 31) / 32) + DS_WARPS - 1) / DS_WARPS; // one warp per 32 x 32 tile
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->prop.multiProcessorCount * 24);
+    // elements for the BTRS kernel: at most every element (8 B each, context scratch)
+    int64_t *biglist = nullptr;
+    BN_TRY(bn_ctx_scratch(ctx, 5, (size_t)G * (size_t)C * 8, (void **)&biglist));
+    DevBuf<unsigned long long> bigcount;
+    BN_TRY(bigcount.alloc(ctx, 1));
+    BN_CUDA(ctx, cudaMemsetAsync(bigcount.p, 0, 8, ctx->stream));
+    const size_t ds_smem = (size_t)DS_WARPS * 32 * 33 * sizeof(double);
+    BN_CUDA(ctx, cudaFuncSetAttribute(k_downsample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds_smem));
+    BN_LAUNCH(ctx, k_downsample, grid, DS_WARPS * 32, ds_smem, G, C, a.p, b.p, bn_philox_keys(seed), o.p, biglist, bigcount.p);
+    BN_LAUNCH(ctx, k_downsample_big, ctx->prop.multiProcessorCount * 8, 256, 0, G, a.p, b.p, seed, biglist, bigcount.p, o.p);
     BN_TRY(o.commit(ctx));
     return bn_sync(ctx);
 }

@@ -83,6 +83,40 @@ static inline PhiloxKeys bn_philox_keys(uint64_t seed)
     return K;
 }
 #ifdef __CUDACC__
+// The same round keys computed on the device from the seed (kernels that take the seed as a plain argument): the
+// adds are warp-uniform, so they run on the uniform datapath once per kernel.
+struct PhiloxKeysDev {
+    uint32_t k[20];
+    __device__ __forceinline__ explicit PhiloxKeysDev(uint64_t seed)
+    {
+        uint32_t x0 = (uint32_t)seed, x1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            k[2 * r] = x0;
+            k[2 * r + 1] = x1;
+            x0 += 0x9E3779B9u;
+            x1 += 0xBB67AE85u;
+        }
+    }
+    __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t &o0, uint32_t &o1,
+                                          uint32_t &o2, uint32_t &o3) const
+    {
+        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint64_t m0 = (uint64_t)0xD2511F53u * a0, m1 = (uint64_t)0xCD9E8D57u * a2;
+            const uint32_t n0 = (uint32_t)(m1 >> 32) ^ a1 ^ k[2 * r], n2 = (uint32_t)(m0 >> 32) ^ a3 ^ k[2 * r + 1];
+            a1 = (uint32_t)m1;
+            a3 = (uint32_t)m0;
+            a0 = n0;
+            a2 = n2;
+        }
+        o0 = a0;
+        o1 = a1;
+        o2 = a2;
+        o3 = a3;
+    }
+};
 __device__ __forceinline__ void bn_philox_block(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                 uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
 {
