@@ -641,7 +641,8 @@ int bn_mat_ensure_blockptr(bn_ctx *ctx, const bn_mat *cm)
 {
     bn_mat *m = const_cast<bn_mat *>(cm); // a cache, like the gene-major twin
     if (m->blockptr) return BN_OK;
-    if (m->nnz >= 4294967295LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard");
+    // positions are 32-bit in the posterior kernels, which also look up to 6 x 32 entries past a slice start
+    if (m->nnz >= 4294967295LL - 4096) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 - 4096 per shard");
     cudaSetDevice(ctx->device);
     m->nblock = (m->G + BN_ROWBLOCK - 1) / BN_ROWBLOCK;
     BN_CUDA(ctx, cudaMallocAsync((void **)&m->blockptr, (size_t)(m->nblock + 1) * (size_t)m->C * 4, ctx->stream));
