@@ -935,3 +935,42 @@ def test_fit_2d_analytic_gradient_and_prior_fun(bn, ctx, oracle, small):
     g = int(np.argmax((X > 0).sum(axis=1)))
     par = np.array([P["BB_prior"]["size"][g] * 1.3, P["BB_prior"]["mu"][g] * 0.8])
     np.testing.assert_allclose(bn.GradientFun_NB_2D(par, X[g], beta, ctx=ctx), oracle.GradientFun_NB_2D(par, X[g], beta), rtol=1e-9)
+
+
+# ------------------------------------------------------------------------ randomized shapes
+def test_random_shapes_and_column_blocks(bn, ctx, oracle):
+    """Posterior mean / mode (bit-exact), draws (support, purity across column blocks) and DownSampling (support) on
+    random shapes around the kernels' block sizes (128-gene row blocks, 1024-gene CTAs, 32 x 32 tiles, 64-column
+    chunks), densities from 1 % to 70 %, with empty columns/rows and arbitrary column sub-blocks."""
+    rng = np.random.default_rng(2026)
+    shapes = [(127, 33), (128, 64), (129, 65), (255, 31), (1024, 40), (1151, 70), (1153, 129), (2050, 17), (300, 200), (96, 257)]
+    for n, (G, C) in enumerate(shapes):
+        dens = [0.01, 0.08, 0.3, 0.7][n % 4]
+        X = (rng.random((G, C)) < dens) * rng.integers(1, 30, (G, C)).astype(np.float64)
+        X[:, rng.integers(0, C)] = 0
+        X[rng.integers(0, G), :] = 0
+        beta = rng.uniform(0.02, 0.6, C)
+        size = rng.uniform(0.1, 5, G)
+        mu = rng.uniform(0.0, 20, G)
+        Mo = oracle.CSC.from_dense(X)
+        M = bn.Check_input(X, ctx)
+        wmean, wmode = oracle.Main_mean_NB_Bay(Mo, beta, size, mu), oracle.Main_mode_NB_Bay(Mo, beta, size, mu)
+        assert np.array_equal(bn.Main_mean_NB_Bay(M, beta, size, mu), wmean), (G, C)
+        assert np.array_equal(bn.Main_mode_NB_Bay(M, beta, size, mu), wmode), (G, C)
+        c0 = int(rng.integers(0, C - 1))
+        nc = int(rng.integers(1, C - c0 + 1))
+        assert np.array_equal(bn.Main_mode_NB_Bay(M, beta, size, mu, col0=c0, ncol=nc), wmode[:, c0:c0 + nc]), (G, C, c0, nc)
+        assert np.array_equal(bn.Main_mean_NB_Bay(M, beta, size, mu, col0=c0, ncol=nc), wmean[:, c0:c0 + nc]), (G, C, c0, nc)
+        d = bn.Main_NB_Bay(M, beta, size, mu, S=5, seed=9)
+        assert d.shape == (G, C, 5) and np.array_equal(d, np.floor(d)) and (d >= X[:, :, None]).all()
+        assert (d[mu == 0] == X[mu == 0][:, :, None]).all()
+        assert np.array_equal(bn.Main_NB_Bay(M, beta, size, mu, S=5, seed=9, col0=c0, ncol=nc), d[:, c0:c0 + nc, :]), (G, C, c0, nc)
+        ds = bn.DownSampling(X, beta, seed=4, ctx=ctx)
+        assert ds.shape == X.shape and np.array_equal(ds, np.floor(ds)) and (ds >= 0).all() and (ds <= X).all()
+        assert (ds[X == 0] == 0).all()
+        if n % 3 == 0:
+            Xc = X.copy()
+            Xc[0, Xc.sum(axis=0) == 0] = 1.0
+            sc = bn.SyntheticControl(Xc, beta, seed=3, ctx=ctx)
+            np.testing.assert_allclose(sc["lambda"], oracle.SyntheticControl(Xc, beta)["lambda"], rtol=1e-12)
+            assert sc["N_c"].shape == X.shape and (sc["N_c"] >= 0).all() and (sc["N_c"][sc["lambda"] == 0] == 0).all()
