@@ -136,14 +136,14 @@ class ClockSampler:
 
 
 def traffic_from_profiles(config, phase, launches):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the phase's dominant kernel, per launch, from the
-    committed `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py)."""
+    """(bytes, source): dram__bytes_read.sum + dram__bytes_write.sum of the phase's dominant kernel, per launch, from
+    the committed `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py)."""
     try:
         t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
         e = t[str(config)][phase]
-        return {"bytes_per_launch": e["bytes_per_launch"], "kernel": e["kernel"], "source": e["source"]}
+        return e["bytes_per_launch"], "%s, %s" % (e["kernel"], e["source"])
     except Exception:
-        return None
+        return None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -336,14 +336,16 @@ def run_ours(args):
     roof_post = {"kernel": post_kernel, "bound": "hbm", "achieved": post_bytes / post_s / 1e9,
                  "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                  "frac": post_bytes / post_s / 1e9 / hbm_peak,
-                 "traffic": traffic_from_profiles(args.config, "posterior", post_launches), "ms": post_s * 1e3,
+                 "traffic": traffic_from_profiles(args.config, "posterior", post_launches)[0],
+                 "traffic_source": traffic_from_profiles(args.config, "posterior", post_launches)[1], "ms": post_s * 1e3,
                  "algorithmic_bytes": post_bytes, "launches_per_step": post_launches,
                  "write_only_peak_GBs": wp,
                  "frac_of_write_only_peak": post_bytes / post_s / 1e9 / (wp["planes_S_1KB_runs"] if out_kind == "sample" else wp["linear"])}
     roof_fit = {"kernel": "k_fit_size", "bound": "fp64", "achieved": fit_flops / fit_s / 1e12,
                 "peak": fp64_peak.value / 1e12, "peak_source": "measured DFMA micro-benchmark (bn_debug_fp64_peak)",
                 "unit": "TFLOP/s", "frac": fit_flops / fit_s / fp64_peak.value,
-                "traffic": traffic_from_profiles(args.config, "fit", len(Ms)), "ms": fit_s * 1e3,
+                "traffic": traffic_from_profiles(args.config, "fit", len(Ms))[0],
+                "traffic_source": traffic_from_profiles(args.config, "fit", len(Ms))[1], "ms": fit_s * 1e3,
                 "likelihood_terms_per_s": (dense_terms + nz_terms) / fit_s, "evaluations": evals}
     dominant = roof_fit if fit_s >= post_s else roof_post
 
