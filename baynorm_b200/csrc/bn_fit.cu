@@ -566,7 +566,7 @@ struct FitSlot {
     uint32_t tail[FitCfg<256>::HMAX + 1];
 };
 
-template <int MINB, int UNR>
+template <int MINB, int UNR, int NS>
 __global__ void __launch_bounds__(256, MINB)
     k_fit_size_ms(int64_t G, int64_t C, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
                   const double *__restrict__ beta, const double *__restrict__ logbeta, const double *__restrict__ mu0,
@@ -577,20 +577,20 @@ __global__ void __launch_bounds__(256, MINB)
     const double lower = params[0], upper = params[1], beta_max = params[2]; // device-resident: no host round trip
     constexpr int HMAX = FitCfg<256>::HMAX;
     __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
-    __shared__ FitSlot slot[FIT_NS];
-    __shared__ double scratch[FIT_NS][8];
+    __shared__ FitSlot slot[NS];
+    __shared__ double scratch[NS][8];
     __shared__ double red8[8];
     __shared__ int xmax_sh, n_running, queue_dry; // queue_dry: stop polling the global queue once it is empty
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bn_log_table_load(tab);
-    if (tid < FIT_NS) slot[tid].state = 0;
+    if (tid < NS) slot[tid].state = 0;
     if (tid == 0) queue_dry = 0;
     __syncthreads();
     for (;;) {
         // ---- refill idle slots (thread 0); all-zero genes are answered on the spot -------------
         if (tid == 0) {
             int running = 0;
-            for (int s = 0; s < FIT_NS; s++) {
+            for (int s = 0; s < NS; s++) {
                 FitSlot &sl = slot[s];
                 while (sl.state == 0 && !queue_dry) {
                     const unsigned long long gq = atomicAdd(queue, 1ULL);
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(256, MINB)
         __syncthreads();
         if (n_running == 0) break;
         // ---- prologue of fresh slots: count histogram -> tail table, Kc, largest count ---------
-        for (int s = 0; s < FIT_NS; s++) {
+        for (int s = 0; s < NS; s++) {
             FitSlot &sl = slot[s];
             if (sl.state != 1) continue; // uniform
             for (int q = tid; q <= HMAX; q += 256) sl.tail[q] = 0;
@@ -661,10 +661,10 @@ __global__ void __launch_bounds__(256, MINB)
             __syncthreads();
         }
         // ---- one sweep: l(next) of every running slot ------------------------------------------
-        double r[FIT_NS], pa[FIT_NS], pb[FIT_NS], acc[FIT_NS];
+        double r[NS], pa[NS], pb[NS], acc[NS];
         bool any_slow = false;
 #pragma unroll
-        for (int s = 0; s < FIT_NS; s++) {
+        for (int s = 0; s < NS; s++) {
             r[s] = (slot[s].state == 2) ? slot[s].mu / slot[s].next : 0.0;
             pa[s] = 1.0;
             pb[s] = 1.0;
@@ -679,13 +679,13 @@ __global__ void __launch_bounds__(256, MINB)
                 for (int it = 0; it < 16; it++) {
                     const double b0 = __ldg(beta + j + it * 512), b1 = __ldg(beta + j + it * 512 + 256);
 #pragma unroll
-                    for (int s = 0; s < FIT_NS; s++) {
+                    for (int s = 0; s < NS; s++) {
                         pa[s] *= fma(r[s], b0, 1.0);
                         pb[s] *= fma(r[s], b1, 1.0);
                     }
                 }
 #pragma unroll
-                for (int s = 0; s < FIT_NS; s++) {
+                for (int s = 0; s < NS; s++) {
                     acc[s] += bn_log(pa[s], tab) + bn_log(pb[s], tab);
                     pa[s] = 1.0;
                     pb[s] = 1.0;
@@ -694,19 +694,19 @@ __global__ void __launch_bounds__(256, MINB)
             for (; j < C; j += 256) { // fewer than 32 factors left per thread
                 const double b0 = __ldg(beta + j);
 #pragma unroll
-                for (int s = 0; s < FIT_NS; s++) pa[s] *= fma(r[s], b0, 1.0);
+                for (int s = 0; s < NS; s++) pa[s] *= fma(r[s], b0, 1.0);
             }
         } else { // absurd mu/size ratios: one logarithm per cell keeps everything finite
             for (int64_t j = tid; j < C; j += 256) {
                 const double b0 = __ldg(beta + j);
 #pragma unroll
-                for (int s = 0; s < FIT_NS; s++) acc[s] += bn_log(fma(r[s], b0, 1.0), tab);
+                for (int s = 0; s < NS; s++) acc[s] += bn_log(fma(r[s], b0, 1.0), tab);
             }
         }
 #pragma unroll
-        for (int s = 0; s < FIT_NS; s++) acc[s] += bn_log(pa[s], tab) + bn_log(pb[s], tab);
+        for (int s = 0; s < NS; s++) acc[s] += bn_log(pa[s], tab) + bn_log(pb[s], tab);
 #pragma unroll 1
-        for (int s = 0; s < FIT_NS; s++) {
+        for (int s = 0; s < NS; s++) {
             const FitSlot &sl = slot[s];
             if (sl.state != 2) continue; // uniform
             const double phi = sl.next, mu = sl.mu;
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(256, MINB)
         }
         __syncthreads();
         // ---- thread s steps the solver of slot s ------------------------------------------------
-        if (tid < FIT_NS && slot[tid].state == 2) {
+        if (tid < NS && slot[tid].state == 2) {
             FitSlot &sl = slot[tid];
             double tot = 0.0;
 #pragma unroll
@@ -1313,9 +1313,17 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
             BN_TRY(strag.alloc(ctx, (size_t)m->G));
             BN_TRY(nstrag.alloc(ctx, 1));
             BN_CUDA(ctx, cudaMemsetAsync(nstrag.p, 0, 4, ctx->stream));
-            // 4 resident CTAs per SM (64 registers): measured 5-9 % faster than 3 x 78 registers, 2 x 112 is 25 % slower
-            BN_LAUNCH(ctx, (k_fit_size_ms<4, 4>), (int)std::min<int64_t>((m->G + FIT_NS - 1) / FIT_NS, (int64_t)sms * 4), 256, 0,
-                      FIT_ARGS, strag.p, nstrag.p);
+            // Sparse single-cell matrices: 4 genes per sweep at 4 resident CTAs per SM (64 registers; measured 5-9 % faster
+            // than 3 x 78 registers, 2 x 112 is 25 % slower).  Dense matrices (>= 20 % non-zero), where the per-gene
+            // non-zero loop dominates and BETA re-use across genes matters less: 2 genes per sweep at 6 CTAs per SM
+            // (40 registers) is 3.5 % faster; 3 x 5 and 6 x 3 are slower on both.
+            const bool dense = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+            if (dense)
+                BN_LAUNCH(ctx, (k_fit_size_ms<6, 4, 2>), (int)std::min<int64_t>((m->G + 1) / 2, (int64_t)sms * 6), 256, 0, FIT_ARGS,
+                          strag.p, nstrag.p);
+            else
+                BN_LAUNCH(ctx, (k_fit_size_ms<4, 4, 4>), (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 4), 256, 0, FIT_ARGS,
+                          strag.p, nstrag.p);
             const int nclusters = std::max(1, sms / FIT_CL - 2);
             BN_LAUNCH(ctx, k_fit_cluster, nclusters * FIT_CL, FIT_CL_THREADS, 0, m->C, m->rowptr, m->gm, d_beta, o, strag.p,
                       nstrag.p, d_size_out, d_conv, d_nfe);
