@@ -27,7 +27,7 @@ class BayNormError(RuntimeError):
 class FitOpts(C.Structure):
     _fields_ = [("method", C.c_int32), ("maxfeval", C.c_int32), ("maxit", C.c_int32), ("M", C.c_int32),
                 ("ftol", C.c_double), ("gtol", C.c_double), ("eps", C.c_double), ("xatol", C.c_double),
-                ("use_gradient", C.c_int32), ("reserved", C.c_int32)]
+                ("use_gradient", C.c_int32), ("park_after", C.c_int32)]
 
 
 class PriorOut(C.Structure):
@@ -85,6 +85,8 @@ SIGNATURES = {
     "bn_synthetic_control": (C.c_int, [_VP, _VP, _VP, _U64, _VP, _VP]),
     "bn_beta_fun": (C.c_int, [_VP, _VP, _D, _VP, _VP, _VP]),
     "bn_debug_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "bn_debug_last_fit": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "bn_debug_tune": (C.c_int, [_VP, C.c_int, C.c_int]),
     "bn_debug_write_peak": (C.c_int, [_VP, _I64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 

@@ -116,6 +116,16 @@ class Context:
         self.check(self.lib.bn_ctx_device_info(self.h, out))
         return {"sms": out[0], "clock_khz": out[1], "cc": out[2], "mem_bytes": out[3]}
 
+    def last_fit(self):
+        """What the last likelihood fit launched: kernel variant, genes parked for the cluster kernel, ..."""
+        out = (C.c_int64 * 4)()
+        self.check(self.lib.bn_debug_last_fit(self.h, out))
+        return {"variant": int(out[0]), "parked": int(out[1]), "park_after": int(out[2]), "analytic_gradient": bool(out[3])}
+
+    def tune(self, knob, value):
+        """Profiling A/B switch (bn_debug_tune); knob is one of TUNE_* below, value 0 restores the default."""
+        self.check(self.lib.bn_debug_tune(self.h, int(knob), int(value)))
+
     def set_allreduce(self, fn, rank, world):
         """fn(buf_ptr:int, count:int, dtype:int, op:int, stream_ptr:int) -> int (0 = ok)."""
         if fn is None:
@@ -426,18 +436,22 @@ def SyntheticControl(Data, BETA_vec, seed=None, ctx=None):
 # --------------------------------------------------------------------------------------
 # R-level functions
 # --------------------------------------------------------------------------------------
-def _fit_opts(GR=False, method="spg", maxfeval=500):
+TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS = 0, 1, 2
+
+
+def _fit_opts(GR=False, method="spg", maxfeval=500, park_after=0):
     o = FitOpts()
     _lib.load().bn_fit_opts_default(C.byref(o))
     o.method = {"spg": 0, "brent": 1}[method]
     o.maxfeval = int(maxfeval)
     o.use_gradient = 1 if GR else 0
+    o.park_after = int(park_after)
     return o
 
 
 def BB_Fun(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, MU_lower=0.01, MU_upper=500, SIZE_lower=0.01,
            SIZE_upper=30, parallel=False, NCores=5, FIX_MU=True, GR=False, method="spg", ctx=None,
-           return_info=False):
+           return_info=False, park_after=0):
     """R/PRIOR_FUNCTIONS.R:380-549.  `parallel`/`NCores` are accepted and ignored: the fit of
     all genes is one kernel launch.  FIX_MU=False returns the G x 2 matrix (size, mu) of the
     reference (:543-546), fitted in the box of its parallel=TRUE branch (:414-419)."""
@@ -447,7 +461,7 @@ def BB_Fun(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, MU_lower=0.01, MU_u
     out = np.zeros(M.G, _F64)
     conv = np.zeros(M.G, np.int32)
     nfe = np.zeros(M.G, np.int32)
-    o = _fit_opts(GR, method)
+    o = _fit_opts(GR, method, park_after=park_after)
     if not FIX_MU:
         mu_out = np.zeros(M.G, _F64)
         ctx.check(ctx.lib.bn_fit_size_mu(ctx.h, M.h, _ptr(b), _ptr(mu0), _ptr(s0), float(SIZE_lower), float(SIZE_upper),

@@ -58,6 +58,8 @@ int bn_ctx_create(int device, bn_ctx **out)
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
     cudaHostAlloc((void **)&c->pinned, 64 * sizeof(double), cudaHostAllocDefault);
+    c->fit_parked = reinterpret_cast<unsigned int *>(c->pinned + 40);
+    *c->fit_parked = 0;
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -220,7 +222,6 @@ extern "C" int bn_mat_from_csc(bn_ctx *ctx, int64_t G, int64_t C, const void *p,
     }
     if (nnz < 0) return bn_fail(ctx, BN_ERR_INVALID, "negative nnz");
     if (nnz > 0 && (!i || !x)) return bn_fail(ctx, BN_ERR_INVALID, "i/x missing");
-    if (nnz >= 4294967295LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard: split the matrix by gene blocks");
     bn_mat *m = new bn_mat();
     m->ctx = ctx;
     m->G = G;
@@ -331,7 +332,6 @@ extern "C" int bn_mat_from_dense(bn_ctx *ctx, int64_t G, int64_t C, const double
     if ((e = cudaMemcpyAsync(&nnz, m->colptr + C, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_CUDA, "dense scan: %s", cudaGetErrorString(e)));
-    if (nnz >= 4294967295LL) return fail(bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard"));
     m->nnz = nnz;
     if ((e = cudaMallocAsync((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
         (e = cudaMallocAsync((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)
@@ -379,6 +379,7 @@ extern "C" int bn_mat_drop_gene_major(bn_mat *m)
 {
     if (!m) return BN_ERR_INVALID;
     m->has_csr = false; // the buffers stay with the matrix: the rebuild overwrites them in place
+    m->has_blockptr = false; // the blocked column pointers are part of the build (and shared with the posterior kernels)
     return BN_OK;
 }
 
@@ -555,71 +556,12 @@ extern "C" int bn_mat_select_cols(bn_ctx *ctx, const bn_mat *m, const int64_t *i
 }
 
 // ---------------------------------------------------------------------------------
-// gene-major twin: stable radix sort of (row, position) pairs, then a gather.
-// Stable => cells stay in increasing order inside each gene => every per-gene
-// reduction has one fixed summation order, independent of launch geometry.
-// ---------------------------------------------------------------------------------
-__global__ void k_iota_u32(uint32_t *__restrict__ v, int64_t n)
-{
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n) v[k] = (uint32_t)k;
-}
-
-// Row pointer from the SORTED row keys: position k opens every row in (key[k-1], key[k]]; rows after the last
-// key are empty.  One coalesced 4 B read per non-zero (a histogram with atomics took 4x as long).
-__global__ void __launch_bounds__(256) k_rowptr_from_sorted(const int32_t *__restrict__ key, int64_t nnz, int64_t G,
-                                                            int64_t *__restrict__ rowptr)
-{
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += gridDim.x * (int64_t)blockDim.x) {
-        const int32_t cur = __ldg(key + k), prev = k > 0 ? __ldg(key + k - 1) : -1;
-        for (int32_t r = prev + 1; r <= cur; r++) rowptr[r] = k;
-        if (k == nnz - 1)
-            for (int64_t r = (int64_t)cur + 1; r <= G; r++) rowptr[r] = nnz;
-    }
-}
-
-__global__ void k_csr_gather(int64_t nnz, int64_t C, const uint32_t *__restrict__ pos, const int64_t *__restrict__ colptr,
-                             const double *__restrict__ val, int32_t *__restrict__ cell, double *__restrict__ rval)
-{
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * (int64_t)blockDim.x) {
-        const int64_t k = pos[q];
-        // column of position k: last j with colptr[j] <= k
-        int64_t lo = 0, hi = C; // invariant: colptr[lo] <= k < colptr[hi]
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (colptr[mid] <= k) lo = mid;
-            else hi = mid;
-        }
-        cell[q] = (int32_t)lo;
-        rval[q] = val[k];
-    }
-}
-
-// (cell << 32) | count for every non-zero, in CSC order: one warp per column
-__global__ void __launch_bounds__(256) k_pack_nz(int64_t C, const int64_t *__restrict__ colptr, const double *__restrict__ val,
-                                                 uint64_t *__restrict__ packed)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
-    for (int64_t j = warp; j < C; j += nwarp) {
-        const int64_t a = colptr[j], b = colptr[j + 1];
-        const uint64_t hi = (uint64_t)j << 32;
-        int64_t k = a + lane;
-        for (; k + 96 < b; k += 128) { // four loads in flight per lane
-            const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + 32), v2 = __ldcs(val + k + 64), v3 = __ldcs(val + k + 96);
-            packed[k] = hi | (uint64_t)(uint32_t)v0;
-            packed[k + 32] = hi | (uint64_t)(uint32_t)v1;
-            packed[k + 64] = hi | (uint64_t)(uint32_t)v2;
-            packed[k + 96] = hi | (uint64_t)(uint32_t)v3;
-        }
-        for (; k < b; k += 32) packed[k] = hi | (uint64_t)(uint32_t)__ldcs(val + k);
-    }
-}
-
 // Blocked column pointers: one warp per column walks the (sorted) row indices once and records where every
-// BN_ROWBLOCK-row block starts.  4 B per non-zero read, (G / 128 + 1) * C * 4 B written, once per matrix: it
-// replaces a 12-step binary search per (warp, column) in every posterior launch.
+// BN_ROWBLOCK-row block starts, as an OFFSET from the start of the column (uint32: a column has at most G < 2^31
+// entries, while absolute positions need 64 bits once a shard holds >= 2^32 non-zeros -- BASELINE config 5 on one
+// GPU).  4 B per non-zero read, (G / 128 + 1) * C * 4 B written, once per matrix: it replaces a 12-step binary
+// search per (warp, column) in every posterior launch and gives the gene-major build its row tiles.
+// ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_blockptr(int64_t C, int64_t nblock, const int64_t *__restrict__ colptr,
                                                   const int32_t *__restrict__ rowidx, uint32_t *__restrict__ blockptr)
 {
@@ -627,82 +569,397 @@ __global__ void __launch_bounds__(256) k_blockptr(int64_t C, int64_t nblock, con
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
     for (int64_t j = warp; j < C; j += nwarp) {
         const int64_t a = colptr[j], b = colptr[j + 1];
-        for (int64_t k = a + lane; k < b; k += 32) {
-            const int64_t t = rowidx[k] / BN_ROWBLOCK, tp = (k > a) ? rowidx[k - 1] / BN_ROWBLOCK : -1;
-            for (int64_t q = tp + 1; q <= t; q++) blockptr[q * C + j] = (uint32_t)k; // blocks opened by entry k
+        for (int64_t k0 = a; k0 < b; k0 += 128) { // four loads in flight per lane; the previous entry comes by shuffle
+            int32_t r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) r[u] = (k0 + u * 32 + lane < b) ? __ldg(rowidx + k0 + u * 32 + lane) : 0x7fffffff;
+            int32_t last = (k0 > a) ? __ldg(rowidx + k0 - 1) : -1; // entry before this batch (warp-uniform address)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int32_t prev = __shfl_up_sync(0xffffffffu, r[u], 1);
+                if (lane == 0) prev = last;
+                last = __shfl_sync(0xffffffffu, r[u], 31);
+                const int64_t k = k0 + u * 32 + lane;
+                if (k < b) {
+                    const int t = r[u] / BN_ROWBLOCK, tp = prev < 0 ? -1 : prev / BN_ROWBLOCK;
+                    for (int q = tp + 1; q <= t; q++) blockptr[(int64_t)q * C + j] = (uint32_t)(k - a); // blocks opened by entry k
+                }
+            }
         }
         // blocks after the last entry (and the closing row) are empty: they start at the end of the column
         const int64_t tl = (b > a) ? rowidx[b - 1] / BN_ROWBLOCK : -1;
-        for (int64_t q = tl + 1 + lane; q <= nblock; q += 32) blockptr[q * C + j] = (uint32_t)b;
+        for (int64_t q = tl + 1 + lane; q <= nblock; q += 32) blockptr[q * C + j] = (uint32_t)(b - a);
     }
 }
 
 int bn_mat_ensure_blockptr(bn_ctx *ctx, const bn_mat *cm)
 {
     bn_mat *m = const_cast<bn_mat *>(cm); // a cache, like the gene-major twin
-    if (m->blockptr) return BN_OK;
-    // positions are 32-bit in the posterior kernels, which also look up to 6 x 32 entries past a slice start
-    if (m->nnz >= 4294967295LL - 4096) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 - 4096 per shard");
+    if (m->has_blockptr) return BN_OK;
     cudaSetDevice(ctx->device);
     m->nblock = (m->G + BN_ROWBLOCK - 1) / BN_ROWBLOCK;
-    BN_CUDA(ctx, cudaMallocAsync((void **)&m->blockptr, (size_t)(m->nblock + 1) * (size_t)m->C * 4, ctx->stream));
+    if (!m->blockptr) BN_CUDA(ctx, cudaMallocAsync((void **)&m->blockptr, (size_t)(m->nblock + 1) * (size_t)m->C * 4, ctx->stream));
     const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
     BN_LAUNCH(ctx, k_blockptr, blocks, 256, 0, m->C, m->nblock, m->colptr, m->rowidx, m->blockptr);
+    m->has_blockptr = true;
     return BN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Gene-major twin (what `Data[g, ]` at R/PRIOR_FUNCTIONS.R:442 extracts, for all genes at once): a hand-written
+// stable counting transpose of the CSC arrays.
+//
+// Work unit = (tile of GM_TILE_ROWS rows) x (range of columns), one WARP each.  Row indices are sorted inside a column, so
+// the tile's part of a column is one contiguous slice, and the blocked column pointers give its bounds with two loads.
+// Rows are distinct inside a slice, so the warp advances a per-row cursor in shared memory with plain loads/stores (no
+// atomics) and walks its columns in increasing order: cells come out ascending inside every gene -- the same order a
+// stable sort by row gives, whatever the launch geometry, so every per-gene reduction downstream keeps ONE summation
+// order (bit-reproducible across GPU counts).
+//   pass 1 (k_gm_count):   cnt[p][r] = entries of row r in column range p             reads 4 B per non-zero
+//   k_gm_offsets:          cnt[p][r] -> entries of row r in ranges < p; rowtot[r]     P x G words
+//   exclusive scan of rowtot -> rowptr
+//   pass 2 (k_gm_scatter): position = rowptr[r] + cnt[p][r] + (rank inside the range) reads 12 B, writes 8 B per non-zero
+// 24 B of DRAM traffic per non-zero (+ 4 B for the blocked column pointers, shared with the posterior kernels) against
+// ~64 B for pack + two cub onesweep passes + row-pointer extraction, and no nnz-sized scratch: that is what lets the
+// 3.4e9 non-zeros of BASELINE config 5 (41 GB CSC + 27 GB gene-major) sit on one 180 GB GPU.
+// ---------------------------------------------------------------------------------
+#define GM_TILE_BLOCKS 8                              // row blocks per tile
+#define GM_TILE_ROWS (GM_TILE_BLOCKS * BN_ROWBLOCK)   // 1024 rows: ~84 entries per column slice at 8 % non-zeros
+#define GM_WARPS 8
+#define GM_PF 3                                       // slice entries per lane prefetched one column ahead
+
+// Pass 1: warp per (row tile, fine column range); rows are distinct inside a column slice, so the per-row counters in
+// shared memory take plain increments, one column at a time.
+__global__ void __launch_bounds__(GM_WARPS * 32, 3)
+    k_gm_count(int64_t G, int64_t C, int64_t nblock, int64_t ntile, int P, const int64_t *__restrict__ colptr,
+               const int32_t *__restrict__ rowidx, const uint32_t *__restrict__ blockptr, uint32_t *__restrict__ cnt)
+{
+    extern __shared__ uint32_t s_cnt_all[]; // [GM_WARPS][GM_TILE_ROWS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *cur = s_cnt_all + warp * GM_TILE_ROWS;
+    const int64_t ntask = ntile * P;
+    // neighbouring warps take neighbouring row tiles of the SAME column range: their slices are adjacent in memory
+    for (int64_t task = (int64_t)blockIdx.x * GM_WARPS + warp; task < ntask; task += (int64_t)gridDim.x * GM_WARPS) {
+        const int64_t p = task / ntile, t = task - p * ntile;
+        const int64_t row0 = t * GM_TILE_ROWS;
+        const int nrow = (int)(G - row0 < GM_TILE_ROWS ? G - row0 : GM_TILE_ROWS);
+        const int64_t c0 = C * p / P, c1 = C * (p + 1) / P;
+        const int64_t blo = t * GM_TILE_BLOCKS, bhi = blo + GM_TILE_BLOCKS < nblock ? blo + GM_TILE_BLOCKS : nblock;
+        const uint32_t *bp_lo = blockptr + blo * C, *bp_hi = blockptr + bhi * C;
+        for (int r = lane; r < nrow; r += 32) cur[r] = 0;
+        __syncwarp();
+        // bounds of 32 columns at a time (coalesced), handed out by shuffle; the first GM_PF x 32 row indices of the
+        // next column's slice are loaded while the current column is counted
+        int32_t pr[GM_PF];
+        int64_t ka = 0, kb = 0; // slice of the column held in pr
+        for (int64_t jg = c0; jg < c1; jg += 32) {
+            const int ng = (int)(c1 - jg < 32 ? c1 - jg : 32);
+            int64_t my_a = 0, my_b = 0;
+            if (lane < ng) {
+                const int64_t cs = __ldg(colptr + jg + lane);
+                my_a = cs + __ldg(bp_lo + jg + lane);
+                my_b = cs + __ldg(bp_hi + jg + lane);
+            }
+            for (int jj = 0; jj < ng; jj++) {
+                if (jj == 0) { // first column of the group: nothing was prefetched for it
+                    ka = __shfl_sync(0xffffffffu, my_a, 0);
+                    kb = __shfl_sync(0xffffffffu, my_b, 0);
+#pragma unroll
+                    for (int q = 0; q < GM_PF; q++) pr[q] = (ka + q * 32 + lane < kb) ? __ldg(rowidx + ka + q * 32 + lane) : -1;
+                }
+                int32_t r_[GM_PF];
+#pragma unroll
+                for (int q = 0; q < GM_PF; q++) r_[q] = pr[q];
+                const int64_t a = ka, b = kb;
+                if (jj + 1 < ng) {
+                    ka = __shfl_sync(0xffffffffu, my_a, jj + 1);
+                    kb = __shfl_sync(0xffffffffu, my_b, jj + 1);
+#pragma unroll
+                    for (int q = 0; q < GM_PF; q++) pr[q] = (ka + q * 32 + lane < kb) ? __ldg(rowidx + ka + q * 32 + lane) : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < GM_PF; q++)
+                    if (r_[q] >= 0) cur[r_[q] - (int)row0]++;
+                // a longer slice (dense matrices): the rest straight from memory, four loads in flight per lane
+                for (int64_t k = a + GM_PF * 32 + lane; k < b; k += 128) {
+                    int32_t rr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) rr[u] = (k + u * 32 < b) ? __ldg(rowidx + k + u * 32) : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (rr[u] >= 0) cur[rr[u] - (int)row0]++;
+                }
+                __syncwarp(); // column j's increments are visible before column j + 1 touches the same rows
+            }
+        }
+        for (int r = lane; r < nrow; r += 32) cnt[p * G + row0 + r] = cur[r];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Pass 2, CTA per (row tile, coarse column range).  Scattering one entry at a time (8 B per row per visit) ran at
+// 3-6e10 stores/s whether a warp walked its columns alone (4.0 ms per 1e8 non-zeros: millions of partly written
+// sectors open in L2) or a CTA placed 64 columns together (1.7 ms): the store TRANSACTION rate is the limit.  So the
+// CTA takes as many consecutive columns as fit GS_CAP staged entries (<= 64), transposes that block in shared memory
+// and writes every row's run of entries contiguously (1.1 ms):
+//   a  mask[r] |= 1 << jj for every entry (r, column jj of the block)            (order-free shared-memory atomics)
+//   b  row counts = popc(mask), exclusive scan -> start of every row's run in the stage, advance the global cursors
+//   c  entry (r, jj) -> stage[start[r] + popc(mask[r] & below(jj))]             (rank = columns before jj: ascending cells)
+//   d  stage -> gm, thread per staged entry: a row's run is contiguous on both sides
+// ---------------------------------------------------------------------------------
+#define GS_THREADS 512
+#define GS_CAP 8192
+#define GS_WMAX 64
+#define GS_MINB 2
+
+template <bool PACKED>
+__global__ void __launch_bounds__(GS_THREADS, GS_MINB)
+    k_gm_scatter(int64_t G, int64_t C, int64_t nblock, int64_t ntile, int P, int F, int Q, const int64_t *__restrict__ colptr,
+                 const int32_t *__restrict__ rowidx, const double *__restrict__ val, const uint32_t *__restrict__ blockptr,
+                 const uint32_t *__restrict__ cnt, const int64_t *__restrict__ rowptr, uint64_t *__restrict__ gm,
+                 int32_t *__restrict__ cell, double *__restrict__ rval)
+{
+    extern __shared__ __align__(16) unsigned char gs_smem[];
+    uint64_t *stage = reinterpret_cast<uint64_t *>(gs_smem);                        // [GS_CAP] packed word or value bits
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(stage + GS_CAP); // [GM_TILE_ROWS]
+    int64_t *gcur = reinterpret_cast<int64_t *>(mask + GM_TILE_ROWS);               // [GM_TILE_ROWS] next free position of the row
+    int64_t *gbase = gcur + GM_TILE_ROWS;                                           // [GM_TILE_ROWS] position of stage[e] = gbase[row] + e
+    uint32_t *rstart = reinterpret_cast<uint32_t *>(gbase + GM_TILE_ROWS);          // [GM_TILE_ROWS]
+    uint16_t *srow = reinterpret_cast<uint16_t *>(rstart + GM_TILE_ROWS);           // [GS_CAP]
+    int32_t *scell = reinterpret_cast<int32_t *>(srow + GS_CAP);                    // [GS_CAP] (real-valued matrices only)
+    __shared__ int64_t s_ka[GS_WMAX];
+    __shared__ uint32_t s_len[GS_WMAX];
+    __shared__ uint32_t s_wsum[GS_THREADS / 32];
+    __shared__ int s_W;
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = GS_THREADS / 32, RPT = GM_TILE_ROWS / GS_THREADS; // rows per thread in the scan
+    for (int64_t task = blockIdx.x; task < ntile * Q; task += gridDim.x) {
+        const int64_t q = task / ntile, t = task - q * ntile; // neighbouring CTAs: neighbouring row tiles of the same columns
+        const int64_t row0 = t * GM_TILE_ROWS;
+        const int nrow = (int)(G - row0 < GM_TILE_ROWS ? G - row0 : GM_TILE_ROWS);
+        const int64_t p0 = q * F, p1 = (q + 1) * F < P ? (q + 1) * F : P;
+        const int64_t c0 = C * p0 / P, c1 = C * p1 / P;
+        const int64_t blo = t * GM_TILE_BLOCKS, bhi = blo + GM_TILE_BLOCKS < nblock ? blo + GM_TILE_BLOCKS : nblock;
+        const uint32_t *bp_lo = blockptr + blo * C, *bp_hi = blockptr + bhi * C;
+        __syncthreads();
+        for (int r = tid; r < GM_TILE_ROWS; r += GS_THREADS) {
+            mask[r] = 0ull;
+            gcur[r] = r < nrow ? rowptr[row0 + r] + (int64_t)cnt[p0 * G + row0 + r] : 0;
+        }
+        for (int64_t j0 = c0; j0 < c1;) {
+            // ---- the block: as many columns as fit the stage ---------------------------------------
+            if (warp < 2) {
+                const int jj = tid; // 0..63
+                int64_t ka = 0;
+                uint32_t len = 0;
+                if (j0 + jj < c1) {
+                    const int64_t cs = __ldg(colptr + j0 + jj);
+                    const uint32_t lo = __ldg(bp_lo + j0 + jj), hi = __ldg(bp_hi + j0 + jj);
+                    ka = cs + lo;
+                    len = hi - lo;
+                }
+                uint32_t inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                s_ka[jj] = ka;
+                s_len[jj] = len;
+                asm volatile("bar.sync 1, 64;" ::: "memory"); // the two warps only
+                if (warp == 1) inc += s_wsum[0];
+                // columns whose cumulative length fits: a prefix (lengths are non-negative)
+                const unsigned fits = __ballot_sync(0xffffffffu, inc <= GS_CAP && j0 + jj < c1);
+                if (lane == 0) s_wsum[2 + warp] = (uint32_t)__popc(fits);
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                if (tid == 0) {
+                    int W = (int)s_wsum[2];
+                    if (W == 32) W += (int)s_wsum[3];
+                    s_W = W > 0 ? W : 1; // one column's slice always fits (<= GM_TILE_ROWS <= GS_CAP entries)
+                }
+            }
+            __syncthreads();
+            const int W = s_W;
+            // ---- a: which columns of the block hold each row -----------------------------------------
+            for (int jj = warp; jj < W; jj += NW) {
+                const int64_t ka = s_ka[jj];
+                const uint32_t len = s_len[jj];
+                const unsigned long long bit = 1ull << jj;
+                for (uint32_t i = lane; i < len; i += 256) {
+                    int32_t rr[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) rr[u] = (i + u * 32 < len) ? __ldg(rowidx + ka + i + u * 32) : -1;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (rr[u] >= 0) atomicOr(mask + (rr[u] - (int)row0), bit);
+                }
+            }
+            __syncthreads();
+            // ---- b: run starts (exclusive scan of the row counts), global cursors ---------------------
+            {
+                uint32_t c[RPT], sum = 0;
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    c[i] = (uint32_t)__popcll(mask[tid * RPT + i]);
+                    sum += c[i];
+                }
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t before = 0;
+                for (int w = 0; w < warp; w++) before += s_wsum[w];
+                uint32_t run = before + inc - sum;
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    const int r = tid * RPT + i;
+                    rstart[r] = run;
+                    const int64_t g0 = gcur[r];
+                    gbase[r] = g0 - (int64_t)run;
+                    gcur[r] = g0 + c[i];
+                    run += c[i];
+                }
+                if (tid == GS_THREADS - 1) s_total = run;
+            }
+            __syncthreads();
+            // ---- c: place the entries, cells ascending inside every row -------------------------------
+            for (int jj = warp; jj < W; jj += NW) {
+                const int64_t ka = s_ka[jj];
+                const uint32_t len = s_len[jj];
+                const unsigned long long below = (1ull << jj) - 1ull;
+                const int64_t j = j0 + jj;
+                for (uint32_t i = lane; i < len; i += 128) {
+                    int32_t rr[4];
+                    double vv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        rr[u] = (i + u * 32 < len) ? __ldg(rowidx + ka + i + u * 32) : -1;
+                        vv[u] = (i + u * 32 < len) ? __ldcs(val + ka + i + u * 32) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (rr[u] >= 0) {
+                            const int rl = rr[u] - (int)row0;
+                            const uint32_t e = rstart[rl] + (uint32_t)__popcll(mask[rl] & below);
+                            stage[e] = PACKED ? (((uint64_t)j << 32) | (uint64_t)(uint32_t)vv[u]) : (uint64_t)__double_as_longlong(vv[u]);
+                            srow[e] = (uint16_t)rl;
+                            if (!PACKED) scell[e] = (int32_t)j;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- d: stream the stage out; a row's run is contiguous in the stage and in the output ----
+            {
+                const uint32_t total = s_total;
+                for (uint32_t e = tid; e < total; e += GS_THREADS) {
+                    const int64_t pos = gbase[srow[e]] + (int64_t)e;
+                    if (PACKED) gm[pos] = stage[e];
+                    else {
+                        rval[pos] = __longlong_as_double((long long)stage[e]);
+                        cell[pos] = scell[e];
+                    }
+                }
+                for (int r = tid; r < GM_TILE_ROWS; r += GS_THREADS) mask[r] = 0ull;
+            }
+            __syncthreads();
+            j0 += W;
+        }
+    }
+}
+
+// cnt[p][r] (entries of row r in column range p) -> exclusive prefix over p; rowtot[r] = row length
+__global__ void __launch_bounds__(256) k_gm_offsets(int64_t G, int P, uint32_t *__restrict__ cnt, int64_t *__restrict__ rowtot)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > G) return;
+    if (r == G) {
+        rowtot[G] = 0;
+        return;
+    }
+    int64_t run = 0; // a row has at most C < 2^32 entries: the prefixes fit 32 bits
+    int p = 0;
+    for (; p + 8 <= P; p += 8) { // eight independent loads in flight, then the dependent prefix
+        uint32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = cnt[(int64_t)(p + u) * G + r];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            cnt[(int64_t)(p + u) * G + r] = (uint32_t)run;
+            run += c[u];
+        }
+    }
+    for (; p < P; p++) {
+        const uint32_t c = cnt[(int64_t)p * G + r];
+        cnt[(int64_t)p * G + r] = (uint32_t)run;
+        run += c;
+    }
+    rowtot[r] = run;
 }
 
 int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m)
 {
     if (m->has_csr) return BN_OK;
     cudaSetDevice(ctx->device);
-    const int64_t nnz = m->nnz, G = m->G;
-    if (nnz > 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz > 2^31-1 per shard in the gene-major build");
+    const int64_t nnz = m->nnz, G = m->G, C = m->C;
+    if (C > 4294967295LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "more than 2^32 - 1 cells");
     if (!m->rowptr) BN_CUDA(ctx, cudaMallocAsync((void **)&m->rowptr, (size_t)(G + 1) * 8, ctx->stream));
-    int bits = 1;
-    while ((1LL << bits) < G) bits++;
     if (m->is_count) {
-        // stable sort of (row -> packed (cell, count)) pairs: the sorted values ARE the gene-major matrix
         if (!m->gm) BN_CUDA(ctx, cudaMallocAsync((void **)&m->gm, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
-        if (nnz) {
-            struct { uint64_t *p; } packed;
-            struct { int32_t *p; } kout;
-            BN_TRY(bn_ctx_scratch(ctx, 2, (size_t)nnz * 8, (void **)&packed.p));
-            BN_TRY(bn_ctx_scratch(ctx, 3, (size_t)nnz * 4, (void **)&kout.p));
-            const int blocks = (int)std::min<int64_t>((m->C + 7) / 8, 148 * 16);
-            BN_LAUNCH(ctx, k_pack_nz, blocks, 256, 0, m->C, m->colptr, m->val, packed.p);
-            size_t tb = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb, (const int32_t *)m->rowidx, kout.p, (const uint64_t *)packed.p, m->gm,
-                                            (int)nnz, 0, bits, ctx->stream);
-            struct { char *p; } tmp;
-            BN_TRY(bn_ctx_scratch(ctx, 4, tb, (void **)&tmp.p));
-            BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p,
-                                                         (const uint64_t *)packed.p, m->gm, (int)nnz, 0, bits, ctx->stream));
-            ctx->launches += (bits + 7) / 8 + 1;
-            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)std::min<int64_t>((nnz + 255) / 256, 148 * 32), 256, 0, kout.p, nnz, G, m->rowptr);
-        }
     } else {
         if (!m->cell) BN_CUDA(ctx, cudaMallocAsync((void **)&m->cell, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
         if (!m->rval) BN_CUDA(ctx, cudaMallocAsync((void **)&m->rval, (size_t)(nnz ? nnz : 1) * 8, ctx->stream));
-        if (nnz) {
-            DevBuf<int32_t> kout;
-            DevBuf<uint32_t> v0, v1;
-            BN_TRY(kout.alloc(ctx, (size_t)nnz));
-            BN_TRY(v0.alloc(ctx, (size_t)nnz));
-            BN_TRY(v1.alloc(ctx, (size_t)nnz));
-            BN_LAUNCH(ctx, k_iota_u32, (unsigned)((nnz + 255) / 256), 256, 0, v0.p, nnz);
-            size_t tb = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb, (const int32_t *)m->rowidx, kout.p, (const uint32_t *)v0.p, v1.p,
-                                            (int)nnz, 0, bits, ctx->stream);
-            DevBuf<char> tmp;
-            BN_TRY(tmp.alloc(ctx, tb));
-            BN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const int32_t *)m->rowidx, kout.p, (const uint32_t *)v0.p,
-                                                         v1.p, (int)nnz, 0, bits, ctx->stream));
-            ctx->launches += (bits + 7) / 8 + 1;
-            BN_LAUNCH(ctx, k_rowptr_from_sorted, (unsigned)std::min<int64_t>((nnz + 255) / 256, 148 * 32), 256, 0, kout.p, nnz, G, m->rowptr);
-            BN_LAUNCH(ctx, k_csr_gather, 148 * 8, 256, 0, nnz, m->C, v1.p, m->colptr, m->val, m->cell, m->rval);
-        }
     }
-    if (!nnz) BN_CUDA(ctx, cudaMemsetAsync(m->rowptr, 0, (size_t)(G + 1) * 8, ctx->stream));
+    if (!nnz) {
+        BN_CUDA(ctx, cudaMemsetAsync(m->rowptr, 0, (size_t)(G + 1) * 8, ctx->stream));
+        m->has_csr = true;
+        return BN_OK;
+    }
+    BN_TRY(bn_mat_ensure_blockptr(ctx, m));
+    const int sms = ctx->prop.multiProcessorCount;
+    const int64_t ntile = (G + GM_TILE_ROWS - 1) / GM_TILE_ROWS;
+    // column ranges: enough (tile, range) warps to fill the device 3 CTAs deep, at least 64 columns per range
+    int64_t P = ((int64_t)sms * 3 * GM_WARPS * 2 + ntile - 1) / ntile;
+    P = std::max<int64_t>(1, std::min<int64_t>(P, (C + 63) / 64));
+    struct { uint32_t *p; } cnt;
+    struct { int64_t *p; } rowtot;
+    struct { char *p; } tmp;
+    BN_TRY(bn_ctx_scratch(ctx, 2, (size_t)P * (size_t)G * 4, (void **)&cnt.p));
+    BN_TRY(bn_ctx_scratch(ctx, 3, (size_t)(G + 1) * 8, (void **)&rowtot.p));
+    const size_t smem = (size_t)GM_WARPS * GM_TILE_ROWS * sizeof(uint32_t);
+    const int grid = (int)std::min<int64_t>((ntile * P + GM_WARPS - 1) / GM_WARPS, (int64_t)sms * 3);
+    BN_LAUNCH(ctx, k_gm_count, grid, GM_WARPS * 32, smem, G, C, m->nblock, ntile, (int)P, m->colptr, m->rowidx, m->blockptr, cnt.p);
+    BN_LAUNCH(ctx, k_gm_offsets, (unsigned)((G + 1 + 255) / 256), 256, 0, G, (int)P, cnt.p, rowtot.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, rowtot.p, m->rowptr, (int)(G + 1), ctx->stream);
+    BN_TRY(bn_ctx_scratch(ctx, 4, tb, (void **)&tmp.p));
+    BN_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, rowtot.p, m->rowptr, (int)(G + 1), ctx->stream));
+    ctx->launches++;
+    {
+        // pass 2: CTAs over (row tile, coarse range of F fine column ranges), about two waves of GS_MINB CTAs per SM
+        const int64_t want = (int64_t)sms * GS_MINB * 2;
+        int64_t Q = std::max<int64_t>(1, std::min<int64_t>(P, (want + ntile - 1) / ntile));
+        const int64_t F = (P + Q - 1) / Q;
+        Q = (P + F - 1) / F;
+        const size_t smem2 = (size_t)GS_CAP * 8 + (size_t)GM_TILE_ROWS * (8 + 8 + 8 + 4) + (size_t)GS_CAP * 2 + (m->is_count ? 0 : (size_t)GS_CAP * 4);
+        const int grid2 = (int)std::min<int64_t>(ntile * Q, (int64_t)sms * GS_MINB);
+#define GS_ARGS G, C, m->nblock, ntile, (int)P, (int)F, (int)Q, m->colptr, m->rowidx, m->val, m->blockptr, cnt.p, m->rowptr, m->gm, m->cell, m->rval
+        if (m->is_count) {
+            BN_CUDA(ctx, cudaFuncSetAttribute(k_gm_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            BN_LAUNCH(ctx, (k_gm_scatter<true>), grid2, GS_THREADS, smem2, GS_ARGS);
+        } else {
+            BN_CUDA(ctx, cudaFuncSetAttribute(k_gm_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            BN_LAUNCH(ctx, (k_gm_scatter<false>), grid2, GS_THREADS, smem2, GS_ARGS);
+        }
+#undef GS_ARGS
+    }
     m->has_csr = true;
     return BN_OK;
 }

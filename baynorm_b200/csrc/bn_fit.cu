@@ -169,7 +169,7 @@ template <int TPG> __device__ double nb_loglik_grad(const FitGene &g, double phi
 // control$maximize = TRUE, so the objective is func = -l.
 // ---------------------------------------------------------------------------------
 struct FitOpts {
-    int method, maxfeval, maxit, M, use_gradient;
+    int method, maxfeval, maxit, M, use_gradient, evcap;
     double ftol, gtol, eps, xatol;
 };
 
@@ -463,8 +463,10 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
         g.tail = hist;
         double par = size0[gi], res = par;
         int conv = 0, nfe = 0;
-        if (g.nnz == 0 || !(g.mu > 0.0)) {
-            // flat likelihood (all-zero gene): spg's first projected gradient is 0, it returns the start
+        if (!(g.mu > 0.0)) {
+            // flat likelihood (mean 0: an all-zero gene under the MME start): spg's first projected gradient is 0, it
+            // returns the start.  A gene without stored entries but a caller-supplied mean > 0 is NOT flat
+            // (l = -phi sum log1p(mu beta_j / phi)) and takes the normal path with an empty tail table.
             res = proj(par, lower, upper);
             if (o.method == BN_FIT_SPG) nfe = 2;
         } else {
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
 // fold points and solver path do not depend on which genes share the CTA.
 // ---------------------------------------------------------------------------------
 #define FIT_NS 4
-#define FIT_EVCAP 128      // evaluations after which a gene is handed to the cluster kernel
+#define FIT_EVCAP 128      // default number of evaluations after which a gene is handed to the cluster kernel (bn_fit_opts.park_after)
 #define FIT_CL 8           // CTAs per cluster (portable maximum)
 #define FIT_CL_THREADS 512
 
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(256, MINB)
                     }
                     const int64_t gi = (int64_t)gq, a = rowptr[gi], n = rowptr[gi + 1] - a;
                     const double mu = mu0[gi];
-                    if (n == 0 || !(mu > 0.0)) { // flat likelihood: spg returns the projected start
+                    if (!(mu > 0.0)) { // flat likelihood (mean 0): spg returns the projected start
                         size_out[gi] = proj(size0[gi], lower, upper);
                         if (conv_out) conv_out[gi] = 0;
                         if (nfe_out) nfe_out[gi] = (o.method == BN_FIT_SPG) ? 2 : 0;
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(256, MINB)
             pa[s] = 1.0;
             pb[s] = 1.0;
             acc[s] = 0.0;
-            any_slow |= !(fma(r[s], beta_max, 1.0) < 9.0e18); // (1 + r beta_max)^16 must stay finite
+            any_slow |= !(fma(r[s], beta_max, 1.0) < 2.0e9); // (1 + r beta_max)^32 must stay finite (remainder loop: < 32 factors)
         }
         if (!any_slow) {
             // blocks of 16 x 512 cells: 32 factors per slot between folds, no branch inside the block
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(256, MINB)
                 if (conv_out) conv_out[sl.gene] = conv;
                 if (nfe_out) nfe_out[sl.gene] = sl.nfe;
                 sl.state = 0;
-            } else if (strag && sl.nfe >= FIT_EVCAP) {
+            } else if (strag && sl.nfe >= o.evcap) {
                 // a straggler (BB::spg may run to maxit = 1500 iterations): one CTA would hold the tail of
                 // the whole launch for milliseconds, so park the solver state for the cluster kernel
                 Straggler &g = strag[atomicAdd(n_strag, 1u)];
@@ -840,7 +842,7 @@ __global__ void __cluster_dims__(FIT_CL, 1, 1) __launch_bounds__(FIT_CL_THREADS,
             if (!(phi > 0.0)) break; // finished (sizes are positive: the box has lower > 0)
             const double r = mu / phi;
             double acc = 0.0, pa = 1.0, pb = 1.0;
-            if (fma(r, 1.0, 1.0) < 9.0e18) {
+            if (fma(r, 1.0, 1.0) < 2.0e9) { // (1 + r)^32 stays finite: the remainder loop multiplies up to 31 factors
                 int64_t j = t;
                 for (; j + 15 * 2 * NT + NT < C; j += 16 * 2 * NT) {
 #pragma unroll 4
@@ -1252,7 +1254,7 @@ extern "C" void bn_fit_opts_default(bn_fit_opts *o)
     o->eps = 1e-7;
     o->xatol = 1e-10;
     o->use_gradient = 0;
-    o->reserved = 0;
+    o->park_after = 0;
 }
 
 // params[0..1] = box: either the host scalars, or (from_mm) derived on the device from
@@ -1285,6 +1287,7 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     o.gtol = od.gtol;
     o.eps = od.eps;
     o.xatol = od.xatol;
+    o.evcap = od.park_after > 0 ? od.park_after : FIT_EVCAP;
     BN_TRY(bn_mat_ensure_csr(ctx, m));
     DevBuf<double> lb;
     BN_TRY(lb.alloc(ctx, (size_t)m->C));
@@ -1298,14 +1301,17 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     BN_LAUNCH(ctx, k_max_vec, 1, 1024, 0, m->C, d_beta, params.p + 2);
     const int sms = ctx->prop.multiProcessorCount;
     const bool grad = o.use_gradient != 0;
+    *ctx->fit_parked = 0;
+    ctx->last_fit[2] = o.evcap;
+    ctx->last_fit[3] = grad ? 1 : 0;
 #define FIT_ARGS m->G, m->C, m->rowptr, m->gm, d_beta, lb.p, d_mu0, d_size0, params.p, o, q.p, d_size_out, d_conv, d_nfe
     if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
         const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);
-        static int single = -1;
-        if (single < 0) single = getenv("BN_FIT_SINGLE_SLOT") ? 1 : 0; // A/B switch for profiling
+        const int force = ctx->tune[BN_TUNE_FIT_VARIANT]; // A/B switch of profiling runs (bn_debug_tune)
+        ctx->last_fit[0] = 1;
         if (grad) BN_LAUNCH(ctx, (k_fit_size<256, true>), grid, 256, 0, FIT_ARGS);
-        else if (single) BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
+        else if (force == 1) BN_LAUNCH(ctx, (k_fit_size<256, false>), grid, 256, 0, FIT_ARGS);
         else {
             // sweep kernel, then the cluster kernel for the genes it parked (usually none or a handful)
             DevBuf<Straggler> strag;
@@ -1317,7 +1323,8 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
             // than 3 x 78 registers, 2 x 112 is 25 % slower).  Dense matrices (>= 20 % non-zero), where the per-gene
             // non-zero loop dominates and BETA re-use across genes matters less: 2 genes per sweep at 6 CTAs per SM
             // (40 registers) is 3.5 % faster; 3 x 5 and 6 x 3 are slower on both.
-            const bool dense = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+            const bool dense = force ? force == 2 : (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+            ctx->last_fit[0] = dense ? 2 : 3;
             if (dense)
                 BN_LAUNCH(ctx, (k_fit_size_ms<6, 4, 2>), (int)std::min<int64_t>((m->G + 1) / 2, (int64_t)sms * 6), 256, 0, FIT_ARGS,
                           strag.p, nstrag.p);
@@ -1327,8 +1334,10 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
             const int nclusters = std::max(1, sms / FIT_CL - 2);
             BN_LAUNCH(ctx, k_fit_cluster, nclusters * FIT_CL, FIT_CL_THREADS, 0, m->C, m->rowptr, m->gm, d_beta, o, strag.p,
                       nstrag.p, d_size_out, d_conv, d_nfe);
+            BN_CUDA(ctx, cudaMemcpyAsync(ctx->fit_parked, nstrag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         }
     } else {
+        ctx->last_fit[0] = 0;
         const int grid = (int)std::min<int64_t>((m->G + 3) / 4, (int64_t)sms * 24);
         if (grad) BN_LAUNCH(ctx, (k_fit_size<32, true>), grid, 128, 0, FIT_ARGS);
         else BN_LAUNCH(ctx, (k_fit_size<32, false>), grid, 128, 0, FIT_ARGS);
@@ -1492,6 +1501,7 @@ extern "C" int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, co
     o.gtol = od.gtol;
     o.eps = od.eps;
     o.xatol = od.xatol;
+    o.evcap = FIT_EVCAP;
     DevIn<double> b, mu0, s0;
     BN_TRY(b.bind(ctx, BETA_vec, (size_t)m->C));
     BN_TRY(mu0.bind(ctx, INITIAL_MU_vec, (size_t)m->G));
@@ -1513,6 +1523,10 @@ extern "C" int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, co
     BN_TRY(q.alloc(ctx, 1));
     BN_CUDA(ctx, cudaMemsetAsync(q.p, 0, 8, ctx->stream));
     const int grid = (int)std::min<int64_t>(m->G, (int64_t)ctx->prop.multiProcessorCount * 4);
+    ctx->last_fit[0] = 4;
+    *ctx->fit_parked = 0;
+    ctx->last_fit[2] = 0;
+    ctx->last_fit[3] = o.use_gradient ? 1 : 0;
     if (o.use_gradient)
         BN_LAUNCH(ctx, k_fit_2d<true>, grid, 256, 0, m->G, m->C, m->rowptr, m->gm, b.p, lb.p, mu0.p, s0.p, box.p, o, q.p, so.p, mo.p,
                   co.p, no.p);
@@ -1524,4 +1538,21 @@ extern "C" int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, co
     BN_TRY(co.commit(ctx));
     BN_TRY(no.commit(ctx));
     return bn_sync(ctx);
+}
+
+extern "C" int bn_debug_last_fit(const bn_ctx *ctx, int64_t out[4])
+{
+    if (!ctx || !out) return BN_ERR_INVALID;
+    out[0] = ctx->last_fit[0];
+    out[1] = (int64_t)*ctx->fit_parked;
+    out[2] = ctx->last_fit[2];
+    out[3] = ctx->last_fit[3];
+    return BN_OK;
+}
+
+extern "C" int bn_debug_tune(bn_ctx *ctx, int knob, int value)
+{
+    if (!ctx || knob < 0 || knob >= BN_TUNE_COUNT) return BN_ERR_INVALID;
+    ctx->tune[knob] = value;
+    return BN_OK;
 }

@@ -30,6 +30,9 @@ struct bn_ctx {
     // pool was measured to stall the host for 5-400 ms every few calls
     void *scratch[8] = {};
     size_t scratch_bytes[8] = {};
+    int tune[BN_TUNE_COUNT] = {};   // bn_debug_tune: A/B switches of profiling runs (0 = default)
+    int64_t last_fit[4] = {};       // bn_debug_last_fit
+    unsigned int *fit_parked = nullptr; // pinned: genes parked by the last sweep kernel
 };
 // returns ctx->scratch[slot] with at least `bytes` bytes (contents undefined)
 int bn_ctx_scratch(bn_ctx *ctx, int slot, size_t bytes, void **out);
@@ -52,10 +55,12 @@ struct bn_mat {
     // general real-valued matrices (EstPrior on already normalised data): separate arrays
     int32_t *cell = nullptr;   // [nnz]
     double *rval = nullptr;    // [nnz]
-    // blocked column pointers (built on demand by bn_mat_ensure_blockptr): blockptr[t * C + j] = first position of
-    // column j whose row is >= t * BN_ROWBLOCK, t = 0 .. nblock (row nblock = colptr[j + 1]).  The posterior
-    // kernels give every warp one row block: its slice of a column is [blockptr[t][j], blockptr[t + 1][j]).
+    // blocked column pointers (built on demand by bn_mat_ensure_blockptr): blockptr[t * C + j] = offset, from the
+    // start colptr[j] of column j, of its first entry whose row is >= t * BN_ROWBLOCK, t = 0 .. nblock (row nblock =
+    // the column length).  The posterior kernels give every warp one row block: its slice of a column is
+    // colptr[j] + [blockptr[t][j], blockptr[t + 1][j]).  Offsets, not positions: a shard may hold >= 2^32 non-zeros.
     uint32_t *blockptr = nullptr; // [(nblock + 1) * C]
+    bool has_blockptr = false;
     int64_t nblock = 0;
 };
 #define BN_ROWBLOCK 128
@@ -120,15 +125,7 @@ template <typename T> struct DevBuf {
         ctx = c;
         n = count;
         if (count == 0) count = 1;
-        static const bool trace = getenv("BN_TRACE_ALLOC") != nullptr;
-        struct timespec t0_, t1_;
-        if (trace) clock_gettime(CLOCK_MONOTONIC, &t0_);
         cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), c->stream);
-        if (trace) {
-            clock_gettime(CLOCK_MONOTONIC, &t1_);
-            const double ms = (t1_.tv_sec - t0_.tv_sec) * 1e3 + (t1_.tv_nsec - t0_.tv_nsec) * 1e-6;
-            if (ms > 0.5) fprintf(stderr, "[bn alloc] %.1f ms for %zu bytes\n", ms, count * sizeof(T));
-        }
         if (e != cudaSuccess) {
             p = nullptr;
             return bn_fail(c, BN_ERR_OOM, "device allocation of %zu bytes failed: %s", count * sizeof(T),

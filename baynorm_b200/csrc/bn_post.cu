@@ -2,14 +2,12 @@
 // Main_NB_Bay; src/bayNorm_main.cpp:1063-1299), binomial DownSampling (:892-915) and the
 // synthetic NB count generator the benchmarks use.
 //
-// Layout: a CTA owns a tile of TG = 2048 consecutive genes and walks NC consecutive cell
-// columns.  size/mu of the tile live in registers for the whole walk.  For every column the
-// CTA scatters that column's non-zeros (row indices are sorted, so the tile's slice is one
-// contiguous run found by binary search) into a shared-memory tile of counts, then every
-// thread evaluates the closed form for its genes and streams the result out: each output
-// element is written exactly once, 256 threads x 8 B contiguous per store instruction.
-// HBM traffic per element: 8 B written + 12 B * nnz-fraction read; beta/size/mu are
-// O(G + C) and stay in L2.
+// Layout: every WARP owns 128 consecutive genes (one row block of the blocked column pointers) and walks a chunk of
+// <= 64 consecutive cell columns without any CTA barrier; size/mu of its genes live in registers for the whole walk.
+// For every column the warp scatters its slice of the column's non-zeros into a 1 KB shared-memory strip of counts,
+// evaluates the closed form for its genes and streams the result out: each output element is written exactly once,
+// 256 contiguous bytes per store instruction.  HBM traffic per element: 8 B written + 12 B * nnz-fraction read;
+// beta/size/mu are O(G + C) and stay in L2.
 //
 // Bit-exactness (mode): the reference's expression order is reproduced with explicit
 // round-to-nearest intrinsics, which the compiler never contracts into FMAs:
@@ -22,7 +20,6 @@
 #include "bn_internal.cuh"
 #include "bn_rng.cuh"
 
-#define POST_THREADS 256
 #define POST_NCMAX 64 // columns walked by one CTA
 
 enum { POST_MEAN = 0, POST_MODE = 1, POST_SAMPLE = 2 };
@@ -60,126 +57,6 @@ __device__ __forceinline__ double post_mode(double x, double size, double mu, do
     return __dadd_rn(floor(__dmul_rn(__ddiv_rn(tm, r), rm1)), x);
 }
 
-// first index in [lo, hi) with rowidx[k] >= key
-__device__ __forceinline__ int64_t lower_bound_row(const int32_t *__restrict__ rowidx, int64_t lo, int64_t hi, int64_t key)
-{
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)__ldg(rowidx + mid) < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
-// Dynamic shared memory: three count tiles of POST_TG doubles.  In iteration jj the CTA
-//   (1) issues the loads of column jj's non-zeros (tile slice) into registers,
-//   (2) computes and stores column jj-1 from tile (jj-1)%3 and zeroes tile (jj+1)%3,
-//   (3) scatters the prefetched non-zeros into tile jj%3 (zeroed one iteration earlier),
-// then one __syncthreads().  Global-load latency of (1) is covered by the arithmetic of (2).
-// POST_PF: non-zeros per thread prefetched two columns ahead (2 covers 512 per tile column: sparse
-// single-cell matrices; 4 covers 1024: dense-ish matrices such as config 2)
-template <int MODE, int POST_EPT, int POST_PF>
-__global__ void __launch_bounds__(POST_THREADS, POST_EPT == 8 ? 3 : 6)
-    k_posterior(int64_t G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
-                const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out,
-                int S, uint64_t seed, int64_t gene0, int64_t cell0, int64_t sstride)
-{
-    constexpr int POST_TG = POST_THREADS * POST_EPT;
-    extern __shared__ double xs[]; // [3][POST_TG]
-    __shared__ int64_t s_lo[POST_NCMAX + 2], s_end[POST_NCMAX + 2];
-    __shared__ double s_beta[POST_NCMAX];
-    const int tid = threadIdx.x;
-    const int64_t t0 = (int64_t)blockIdx.x * POST_TG;
-    const int64_t tend = t0 + POST_TG;
-    const int64_t jb = (int64_t)blockIdx.y * nc_per_cta;
-    const int nc = (int)((jb + nc_per_cta < ncol ? jb + nc_per_cta : ncol) - jb);
-    // every column's slice start, all columns in parallel (one thread each)
-    if (tid < nc) {
-        const int64_t j = col0 + jb + tid;
-        const int64_t cs = __ldg(colptr + j), ce = __ldg(colptr + j + 1);
-        s_lo[tid] = (t0 == 0) ? cs : lower_bound_row(rowidx, cs, ce, t0);
-        s_end[tid] = ce;
-        s_beta[tid] = __ldg(beta + j);
-    } else if (tid < nc + 2) {
-        s_lo[tid] = 0; // empty slices past the chunk keep the pipeline code branch-free
-        s_end[tid] = 0;
-    }
-    double sz[POST_EPT], m[POST_EPT];
-#pragma unroll
-    for (int e = 0; e < POST_EPT; e++) {
-        const int64_t i = t0 + e * POST_THREADS + tid;
-        sz[e] = (i < G) ? __ldg(size + i) : 1.0;
-        m[e] = (i < G) ? __ldg(mu + i) : 0.0;
-    }
-#pragma unroll
-    for (int e = 0; e < POST_EPT; e++) {
-        xs[e * POST_THREADS + tid] = 0.0;
-        xs[POST_TG + e * POST_THREADS + tid] = 0.0;
-    }
-    __syncthreads();
-    // register sets for the slices of two columns in flight (loaded one iteration before use)
-    int32_t prA[POST_PF], prB[POST_PF];
-    double pvA[POST_PF], pvB[POST_PF];
-#define POST_LOAD(PR, PV, COL)                                                           \
-    do {                                                                                 \
-        const int64_t kb_ = s_lo[COL], ke_ = s_end[COL];                                 \
-        _Pragma("unroll") for (int q = 0; q < POST_PF; q++)                              \
-        {                                                                                \
-            const int64_t k = kb_ + q * POST_THREADS + tid;                              \
-            PR[q] = (k < ke_) ? __ldg(rowidx + k) : 0x7fffffff;                          \
-            PV[q] = (k < ke_) ? __ldcs(val + k) : 0.0;                                   \
-        }                                                                                \
-    } while (0)
-    // one pipeline stage: load slice of column jj+1, compute column jj-1, zero tile jj+1, scatter column jj
-#define POST_STAGE(JJ, PR_USE, PV_USE, PR_LOAD, PV_LOAD)                                                 \
-    do {                                                                                                 \
-        const int jj = (JJ);                                                                             \
-        double *xcur = xs + (jj % 3) * POST_TG, *xprev = xs + ((jj + 2) % 3) * POST_TG,                  \
-               *xnext = xs + ((jj + 1) % 3) * POST_TG;                                                   \
-        POST_LOAD(PR_LOAD, PV_LOAD, jj + 1);                                                             \
-        if (jj > 0) {                                                                                    \
-            const int64_t jl = jb + jj - 1;                                                              \
-            const double b = s_beta[jj - 1];                                                             \
-            double *o = out + G * jl;                                                                    \
-            _Pragma("unroll") for (int e = 0; e < POST_EPT; e++)                                         \
-            {                                                                                            \
-                const int64_t i = t0 + e * POST_THREADS + tid;                                           \
-                const double xv = xprev[e * POST_THREADS + tid];                                         \
-                if (i < G) {                                                                             \
-                    if (MODE == POST_MEAN) __stcs(o + i, __dadd_rn(post_tempmu(xv, sz[e], m[e], b), xv)); \
-                    else __stcs(o + i, post_mode(xv, sz[e], m[e], b));                                   \
-                }                                                                                        \
-            }                                                                                            \
-        }                                                                                                \
-        _Pragma("unroll") for (int e = 0; e < POST_EPT; e++) xnext[e * POST_THREADS + tid] = 0.0;        \
-        if (jj < nc) {                                                                                   \
-            bool more = true;                                                                            \
-            _Pragma("unroll") for (int q = 0; q < POST_PF; q++)                                          \
-            {                                                                                            \
-                if ((int64_t)PR_USE[q] < tend) xcur[PR_USE[q] - t0] = PV_USE[q];                         \
-                else more = false;                                                                       \
-            }                                                                                            \
-            if (more) { /* dense tile column: the rest of the slice */                                   \
-                const int64_t ke_ = s_end[jj];                                                           \
-                for (int64_t k = s_lo[jj] + POST_PF * POST_THREADS + tid; k < ke_; k += POST_THREADS) {  \
-                    const int64_t r = __ldg(rowidx + k);                                                 \
-                    if (r >= tend) break;                                                                \
-                    xcur[r - t0] = __ldcs(val + k);                                                      \
-                }                                                                                        \
-            }                                                                                            \
-        }                                                                                                \
-        __syncthreads();                                                                                 \
-    } while (0)
-    POST_LOAD(prA, pvA, 0);
-    for (int j2 = 0; j2 <= nc; j2 += 2) {
-        POST_STAGE(j2, prA, pvA, prB, pvB);
-        if (j2 + 1 <= nc) POST_STAGE(j2 + 1, prB, pvB, prA, pvA);
-    }
-#undef POST_STAGE
-#undef POST_LOAD
-}
-
 // ---------------------------------------------------------------------------------
 // Warp-autonomous posterior mean / mode: every warp owns 32 * EPL consecutive genes (EPL per lane; a store
 // instruction writes 256 contiguous bytes, a column EPL x 256 B) and walks the CTA's column chunk without any
@@ -213,16 +90,23 @@ __global__ void __launch_bounds__(PW_WARPS * 32, MINB)
     const int64_t blk_hi = blk_lo + PW_GENES / BN_ROWBLOCK < nblock ? blk_lo + PW_GENES / BN_ROWBLOCK : nblock; // row nblock = column end
     const uint32_t *bp_lo = blockptr + blk_lo * Ctot + col0 + jb;
     const uint32_t *bp_hi = blockptr + blk_hi * Ctot + col0 + jb;
+    // positions inside the chunk are 32-bit offsets from the chunk's first column (<= 64 columns of < 2^31 rows);
+    // only that base is 64-bit, so a shard may hold more than 2^32 non-zeros
+    const int64_t base = __ldg(colptr + col0 + jb);
+    rowidx += base;
+    val += base;
     uint32_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
     double beta_a = 0.0, beta_b = 0.0;
     if (lane < nc) {
-        lo_a = __ldg(bp_lo + lane);
-        hi_a = __ldg(bp_hi + lane);
+        const uint32_t cs = (uint32_t)(__ldg(colptr + col0 + jb + lane) - base);
+        lo_a = cs + __ldg(bp_lo + lane);
+        hi_a = cs + __ldg(bp_hi + lane);
         beta_a = __ldg(beta + col0 + jb + lane);
     }
     if (lane + 32 < nc) {
-        lo_b = __ldg(bp_lo + lane + 32);
-        hi_b = __ldg(bp_hi + lane + 32);
+        const uint32_t cs = (uint32_t)(__ldg(colptr + col0 + jb + lane + 32) - base);
+        lo_b = cs + __ldg(bp_lo + lane + 32);
+        hi_b = cs + __ldg(bp_hi + lane + 32);
         beta_b = __ldg(beta + col0 + jb + lane + 32);
     }
     double sz[EPL], m[EPL];
@@ -368,16 +252,21 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MINB)
     // slice bounds of columns lane and lane + 32 of the chunk from the blocked column pointers (the warp's 128
     // genes are one row block), and their BETA
     const uint32_t *bp_lo = blockptr + (w0 / BN_ROWBLOCK) * Ctot + col0 + jb;
+    const int64_t base = __ldg(colptr + col0 + jb); // 32-bit offsets from the chunk's first column below
+    rowidx += base;
+    val += base;
     uint32_t lo_a = 0, end_a = 0, lo_b = 0, end_b = 0;
     float beta_a = 0.0f, beta_b = 0.0f;
     if (lane < nc) {
-        lo_a = __ldg(bp_lo + lane);
-        end_a = __ldg(bp_lo + Ctot + lane);
+        const uint32_t cs = (uint32_t)(__ldg(colptr + col0 + jb + lane) - base);
+        lo_a = cs + __ldg(bp_lo + lane);
+        end_a = cs + __ldg(bp_lo + Ctot + lane);
         beta_a = (float)__ldg(beta + col0 + jb + lane);
     }
     if (lane + 32 < nc) {
-        lo_b = __ldg(bp_lo + lane + 32);
-        end_b = __ldg(bp_lo + Ctot + lane + 32);
+        const uint32_t cs = (uint32_t)(__ldg(colptr + col0 + jb + lane + 32) - base);
+        lo_b = cs + __ldg(bp_lo + lane + 32);
+        end_b = cs + __ldg(bp_lo + Ctot + lane + 32);
         beta_b = (float)__ldg(beta + col0 + jb + lane + 32);
     }
     // The draws are made from a float pmf, so the NB parameters size + x and
@@ -830,8 +719,7 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         // repeated with worst-case lists.
         const double rho = (double)m->nnz / ((double)m->G * (double)m->C);
         BN_TRY(bn_mat_ensure_blockptr(ctx, m));
-        const float light_max = getenv("BN_LIGHT_MAX") ? (float)atof(getenv("BN_LIGHT_MAX")) : SAMPLE_LIGHT_MAX;
-        const float light_mass = getenv("BN_LIGHT_MASS") ? (float)atof(getenv("BN_LIGHT_MASS")) : SAMPLE_LIGHT_MASS;
+        const float light_max = SAMPLE_LIGHT_MAX, light_mass = SAMPLE_LIGHT_MASS;
         for (int attempt = 0; attempt < 2; attempt++) {
             const double per_elem = attempt == 0 ? std::min(2.0, std::max(0.125, 6.0 * rho)) : 2.0;
             const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, (int64_t)(((int64_t)1 << 30) / (sizeof(HeavyItem) * per_elem * (double)m->G))));
@@ -851,7 +739,7 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
                 const int64_t nc_ = std::min<int64_t>(chunk, ncol - c0);
                 int ncs = POST_NCMAX; // columns per CTA: short walks keep the columns in flight (and their 20 planes) close together
                 while (ncs > 4 && tiles_s * ((nc_ + ncs - 1) / ncs) < (int64_t)sms * 64) ncs >>= 1;
-                if (const char *e = getenv("BN_SAMPLE_NCS")) ncs = std::max(1, std::min(POST_NCMAX, atoi(e)));
+                if (ctx->tune[BN_TUNE_SAMPLE_NCS] > 0) ncs = std::max(1, std::min(POST_NCMAX, ctx->tune[BN_TUNE_SAMPLE_NCS]));
                 if ((nc_ + ncs - 1) / ncs > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
                 dim3 grid_s((unsigned)tiles_s, (unsigned)((nc_ + ncs - 1) / ncs));
                 BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 2 * sizeof(unsigned int), ctx->stream));
@@ -878,78 +766,26 @@ static int post_launch(bn_ctx *ctx, int mode, const bn_mat *m, const double *BET
         BN_TRY(o.commit(ctx));
         return bn_sync(ctx);
     }
-    static int v1 = -1;
-    if (v1 < 0) v1 = getenv("BN_POST_V1") ? 1 : 0; // A/B switch: the CTA-synchronous kernel below
-    if (!v1) {
-        BN_TRY(bn_mat_ensure_blockptr(ctx, m));
-        const int sms = ctx->prop.multiProcessorCount;
-        const bool densew = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
-        static int epl = 0; // genes per lane: 4 (128 per warp, 4 CTAs per SM; default) or 8 (256 per warp, 3 CTAs per SM)
-        if (!epl) epl = (getenv("BN_POST_EPL") && atoi(getenv("BN_POST_EPL")) == 8) ? 8 : 4;
-        const int64_t PW_TG = 32 * epl * PW_WARPS;
-        const int64_t tiles_w = (m->G + PW_TG - 1) / PW_TG;
-        int ncw = POST_NCMAX;
-        while (ncw > 16 && tiles_w * ((ncol + ncw - 1) / ncw) < (int64_t)sms * 24) ncw >>= 1;
-        if (const char *e = getenv("BN_POST_NCS")) ncw = std::max(1, std::min(POST_NCMAX, atoi(e)));
-        if ((ncol + ncw - 1) / ncw > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * 16);
-        dim3 gridw((unsigned)tiles_w, (unsigned)((ncol + ncw - 1) / ncw));
+    BN_TRY(bn_mat_ensure_blockptr(ctx, m));
+    const int sms = ctx->prop.multiProcessorCount;
+    const bool densew = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+    const int64_t PW_TG = 32 * 4 * PW_WARPS; // 4 genes per lane (128 per warp, 4 CTAs per SM); 8 per lane at 3 CTAs per SM measured slower
+    const int64_t tiles_w = (m->G + PW_TG - 1) / PW_TG;
+    int ncw = POST_NCMAX;
+    while (ncw > 16 && tiles_w * ((ncol + ncw - 1) / ncw) < (int64_t)sms * 24) ncw >>= 1;
+    if (ctx->tune[BN_TUNE_POST_NCS] > 0) ncw = std::max(1, std::min(POST_NCMAX, ctx->tune[BN_TUNE_POST_NCS]));
+    if ((ncol + ncw - 1) / ncw > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * 16);
+    dim3 gridw((unsigned)tiles_w, (unsigned)((ncol + ncw - 1) / ncw));
 #define POSTW_ARGS m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, mm.p, col0, ncol, ncw, o.p, m->blockptr, m->C
-#define POSTW_GO(MODE_, PF_)                                                                                \
-    do {                                                                                                    \
-        if (epl == 4) BN_LAUNCH(ctx, (k_posterior_w<MODE_, PF_, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS); \
-        else BN_LAUNCH(ctx, (k_posterior_w<MODE_, PF_, 3, 8>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);          \
-    } while (0)
-        static int pfd = 0; // slices prefetched per column for >= 20 % dense matrices: 3 x 32 (default) or 5 x 32 non-zeros
-        if (!pfd) pfd = (getenv("BN_POST_PFD") && atoi(getenv("BN_POST_PFD")) == 5) ? 5 : 3;
-        if (mode == POST_MEAN) {
-            if (densew && pfd == 5) POSTW_GO(POST_MEAN, 5);
-            else if (densew) POSTW_GO(POST_MEAN, 3);
-            else POSTW_GO(POST_MEAN, 1);
-        } else {
-            if (densew && pfd == 5) POSTW_GO(POST_MODE, 5);
-            else if (densew) POSTW_GO(POST_MODE, 3);
-            else POSTW_GO(POST_MODE, 1);
-        }
-#undef POSTW_GO
-#undef POSTW_ARGS
-        BN_TRY(o.commit(ctx));
-        return bn_sync(ctx);
-    }
-    static int ept = 0;
-    if (!ept) {
-        const char *e = getenv("BN_POST_EPT");
-        ept = (e && atoi(e) == 4) ? 4 : 8;
-    }
-    const int64_t TG = (int64_t)POST_THREADS * ept;
-    const int64_t tiles = (m->G + TG - 1) / TG;
-    // long column walks amortise the per-CTA slice search and the size/mu loads; keep >= ~8 CTAs per SM
-    int nc = POST_NCMAX;
-    while (nc > 1 && tiles * ((ncol + nc - 1) / nc) < 148 * 8) nc >>= 1;
-    if ((ncol + nc - 1) / nc > 65535) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: at most %d columns per call", 65535 * POST_NCMAX);
-    dim3 grid((unsigned)tiles, (unsigned)((ncol + nc - 1) / nc));
-    const int64_t sstride = m->G * ncol;
-    const size_t smem = 3 * (size_t)TG * sizeof(double);
-    const bool dense = (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
-#define POST_GO2(MODE_, EPT_, PF_)                                                                                   \
-    do {                                                                                                             \
-        BN_CUDA(ctx, cudaFuncSetAttribute(k_posterior<MODE_, EPT_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        BN_LAUNCH(ctx, (k_posterior<MODE_, EPT_, PF_>), grid, POST_THREADS, smem, m->G, m->colptr, m->rowidx, m->val, b.p, sz.p, \
-                  mm.p, col0, ncol, nc, o.p, S, seed, m->gene0, m->cell0, sstride);                                  \
-    } while (0)
-#define POST_GO(MODE_, EPT_)                  \
-    do {                                      \
-        if (dense) POST_GO2(MODE_, EPT_, 4);  \
-        else POST_GO2(MODE_, EPT_, 2);        \
-    } while (0)
-    if (ept == 8) {
-        if (mode == POST_MEAN) POST_GO(POST_MEAN, 8);
-        else POST_GO(POST_MODE, 8);
+    // slices prefetched per column: 3 x 32 non-zeros for >= 20 % dense matrices (5 x 32 spills at 64 registers), 32 otherwise
+    if (mode == POST_MEAN) {
+        if (densew) BN_LAUNCH(ctx, (k_posterior_w<POST_MEAN, 3, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);
+        else BN_LAUNCH(ctx, (k_posterior_w<POST_MEAN, 1, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);
     } else {
-        if (mode == POST_MEAN) POST_GO(POST_MEAN, 4);
-        else POST_GO(POST_MODE, 4);
+        if (densew) BN_LAUNCH(ctx, (k_posterior_w<POST_MODE, 3, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);
+        else BN_LAUNCH(ctx, (k_posterior_w<POST_MODE, 1, 4, 4>), gridw, PW_WARPS * 32, 0, POSTW_ARGS);
     }
-#undef POST_GO
-#undef POST_GO2
+#undef POSTW_ARGS
     BN_TRY(o.commit(ctx));
     return bn_sync(ctx);
 }
@@ -1211,7 +1047,6 @@ extern "C" int bn_mat_synth_nb(bn_ctx *ctx, int64_t G, int64_t C, const double *
     if ((e = cudaMemcpyAsync(&nnz, m->colptr + C, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
         return fail(bn_fail(ctx, BN_ERR_CUDA, "synth scan: %s", cudaGetErrorString(e)));
-    if (nnz >= 4294967295LL) return fail(bn_fail(ctx, BN_ERR_UNSUPPORTED, "nnz >= 2^32 per shard"));
     m->nnz = nnz;
     if ((e = cudaMallocAsync((void **)&m->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream)) != cudaSuccess ||
         (e = cudaMallocAsync((void **)&m->val, (size_t)(nnz ? nnz : 1) * 8, ctx->stream)) != cudaSuccess)

@@ -157,7 +157,9 @@ typedef struct {
     double eps;        /* 1e-7 forward-difference step */
     double xatol;      /* 1e-10 (Brent only) */
     int32_t use_gradient; /* GR=TRUE: analytic GradientFun_NB_1D instead of differences */
-    int32_t reserved;
+    int32_t park_after;   /* long genes (C >= 8192): evaluations after which a gene still running is handed from the
+                             sweep kernel to the cluster kernel; 0 = default (128).  Scheduling only: the solver state
+                             travels with the gene */
 } bn_fit_opts;
 BN_API void bn_fit_opts_default(bn_fit_opts *o);
 /* FIX_MU=TRUE fit of `size` for every gene of the shard: start INITIAL_SIZE_vec[G], mean
@@ -247,6 +249,16 @@ BN_API int bn_debug_fp64_peak(bn_ctx *ctx, double *flops_per_s);
 BN_API int bn_debug_write_peak(bn_ctx *ctx, int64_t bytes, int planes, int run, double *gb_per_s);
 
 /* ---- debug ------------------------------------------------------------------------- */
+/* What the last likelihood fit of this context launched (valid after the call returned):
+ * out[0] = kernel variant (0 warp per gene, 1 CTA per gene, 2 sweep kernel 2 genes x 6 CTAs/SM,
+ *          3 sweep kernel 4 genes x 4 CTAs/SM, 4 the 2-D fit), out[1] = genes the sweep kernel parked for the
+ *          cluster kernel, out[2] = park_after in effect, out[3] = 1 if the analytic gradient was used. */
+BN_API int bn_debug_last_fit(const bn_ctx *ctx, int64_t out[4]);
+/* A/B switches for profiling runs (the product never reads the environment).  value 0 restores the default.
+ *   BN_TUNE_FIT_VARIANT   1..3: force that fit kernel variant for long genes (see bn_debug_last_fit)
+ *   BN_TUNE_SAMPLE_NCS    columns walked per CTA by the 3-D sampler */
+enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_COUNT = 8 };
+BN_API int bn_debug_tune(bn_ctx *ctx, int knob, int value);
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
  * generator against the published known-answer vectors. */
 /* The device logarithms of the likelihood kernels on a vector (which: 0 log, 1 log1p for y >= 0,

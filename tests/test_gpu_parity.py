@@ -261,6 +261,135 @@ def test_fit_spg_against_oracle(bn, ctx, oracle, small, dense50, fixture_data, w
     assert np.array_equal(want == hi, got == hi) and np.array_equal(want == lo, got == lo)
 
 
+@pytest.fixture(scope="module")
+def long_sparse(oracle):
+    """Long genes, single-cell sparsity (C >= 8192, ~8 % non-zero): the shape class of BASELINE configs 3-5, which
+    the launcher sends to the 4-genes-per-sweep kernel (k_fit_size_ms<4,4,4>) and, past park_after evaluations, to
+    the cluster kernel."""
+    X, mu, size, beta = synth_counts(96, 8400, seed=31)
+    Mo = oracle.CSC.from_dense(X)
+    Po = oracle.Prior_fun(Mo, beta, BB_SIZE=False)
+    mu0, s0 = Po["MME_prior"]["MME_MU"], Po["MME_prior"]["MME_SIZE"]
+    # BB_Fun's own default upper bound (R/PRIOR_FUNCTIONS.R:383): 85 % of the genes end strictly inside the box, up to
+    # 129 evaluations per gene (Prior_fun's ceiling(max MME size) = 1 here would leave two thirds of them on the bound)
+    lo, hi = float(s0.min()), 30.0
+    want, conv_o, cnt = oracle.BB_Fun(Mo, beta, mu0, s0, lo, hi, nthreads=8, want_counts=True)
+    assert ((want > lo) & (want < hi)).mean() > 0.7
+    # the reference algorithm against ITSELF with the cells in another order (the same likelihood, summed in a different
+    # order): how far two correct runs of BB::spg on this matrix land apart (tests/test_oracle.py::test_spg_jitter...)
+    jit = []
+    for k in range(2):
+        perm = np.random.default_rng(100 + k).permutation(X.shape[1])
+        w2 = oracle.BB_Fun(oracle.CSC.from_dense(X[:, perm]), beta[perm], mu0, s0, lo, hi, nthreads=8)
+        jit.append(rel_err(w2, want))
+    return dict(X=X, beta=beta, Mo=Mo, mu0=mu0, s0=s0, lo=lo, hi=hi, want=want, conv_o=conv_o, cnt=cnt,
+                jitter_frac=min(float((j <= 1e-6).mean()) for j in jit), jitter_max=max(float(j.max()) for j in jit))
+
+
+def _assert_fit_matches_oracle(oracle, d, got, conv, tag):
+    """The assertions of test_fit_spg_against_oracle on a prepared case."""
+    want, lo, hi, beta, mu0 = d["want"], d["lo"], d["hi"], d["beta"], d["mu0"]
+    re = rel_err(got, want)
+    print("%s: BB_SIZE rel diff GPU vs oracle spg: median %.2e  p99 %.2e  max %.2e; <=1e-6: %.1f%%"
+          % (tag, np.median(re), np.quantile(re, 0.99), re.max(), 100 * (re <= 1e-6).mean()))
+    assert np.array_equal(conv, d["conv_o"])
+    for g in np.argsort(re)[-5:]:
+        fa = oracle.MarginalF_NB_1D(got[g], mu0[g], d["X"][g], beta)
+        fb = oracle.MarginalF_NB_1D(want[g], mu0[g], d["X"][g], beta)
+        assert abs(fa - fb) <= 1e-9 * abs(fb) + 1e-9
+    # North-star tolerance 1e-6 -- up to the jitter of the reference algorithm itself: BB::spg differentiates by forward
+    # differences with eps = 1e-7, so the last bits of l(phi) (summation order) move its stopping point.  The oracle run
+    # on the same matrix with permuted cells agrees with itself to 1e-6 for jitter_frac of the genes (~80 % at 8400
+    # cells) with a maximum of jitter_max; the GPU must be no further from the oracle than the oracle is from itself.
+    print("    oracle vs oracle (cells permuted): <=1e-6 for %.1f%%, max %.2e" % (100 * d["jitter_frac"], d["jitter_max"]))
+    assert (re <= 1e-6).mean() >= min(0.90, d["jitter_frac"] - 0.05)
+    assert re.max() <= max(3.0 * d["jitter_max"], 1e-6)
+    assert ((got >= lo) & (got <= hi)).all()
+    assert np.array_equal(want == hi, got == hi) and np.array_equal(want == lo, got == lo)
+
+
+def test_fit_multislot_sparse_kernel(bn, ctx, oracle, long_sparse):
+    """k_fit_size_ms<4,4,4>: the kernel BASELINE configs 3, 4 and 5 run (R/PRIOR_FUNCTIONS.R:446-456 per gene)."""
+    d = long_sparse
+    assert (d["X"] != 0).mean() < 0.2
+    M = bn.Check_input(d["X"], ctx)
+    got, conv, nfe = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], SIZE_lower=d["lo"], SIZE_upper=d["hi"], return_info=True)
+    info = ctx.last_fit()
+    assert info["variant"] == 3 and info["park_after"] == 128, info
+    _assert_fit_matches_oracle(oracle, d, got, conv, "multi-slot sparse")
+    tot = (d["cnt"][:, 0] + d["cnt"][:, 1]).sum()
+    # evaluation counts: same order, not equal -- near the optimum the oracle's forward-difference gradient is dominated
+    # by the rounding noise of its sequential 8400-term sum (~1e-3 >> gtol), so it stops on ftol a few steps later than
+    # the GPU, whose tree-ordered sums are less noisy
+    print("    evaluations: GPU %d, oracle %d" % (int(nfe.sum()), int(tot)))
+    assert 0.7 * tot <= int(nfe.sum()) <= 1.1 * tot, (int(nfe.sum()), int(tot))
+    # the three kernels that can run these genes are the same function of the data: CTA per gene, 2 per sweep, 4 per sweep
+    for variant in (1, 2):
+        ctx.tune(bn.api.TUNE_FIT_VARIANT, variant)
+        try:
+            alt, conv_a, _ = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], SIZE_lower=d["lo"], SIZE_upper=d["hi"],
+                                       return_info=True)
+            assert ctx.last_fit()["variant"] == variant
+        finally:
+            ctx.tune(bn.api.TUNE_FIT_VARIANT, 0)
+        assert np.array_equal(conv_a, conv)
+        if variant == 2:
+            assert np.array_equal(alt, got)       # same per-thread cell map and summation order: bit-identical
+        else:
+            ra = rel_err(alt, got)
+            assert (ra <= 1e-6).mean() >= d["jitter_frac"] - 0.05 and ra.max() <= 3.0 * d["jitter_max"]
+
+
+@pytest.mark.parametrize("method", ["spg", "brent"])
+def test_fit_cluster_kernel_takes_parked_genes(bn, ctx, oracle, long_sparse, method):
+    """k_fit_cluster: genes still running after park_after evaluations are finished by 8-CTA clusters.  With
+    park_after = 6 nearly every gene is parked mid-solve, so the hand-over of the solver state is what is tested."""
+    d = long_sparse
+    M = bn.Check_input(d["X"], ctx)
+    kw = dict(SIZE_lower=d["lo"], SIZE_upper=d["hi"], return_info=True, method=method)
+    ref, conv_r, nfe_r = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], **kw)
+    assert ctx.last_fit()["parked"] == 0
+    got, conv, nfe = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], park_after=6, **kw)
+    info = ctx.last_fit()
+    assert info["variant"] == 3 and info["park_after"] == 6
+    assert info["parked"] >= 0.5 * int((nfe_r > 6).sum()) > 0, info
+    assert np.array_equal(conv, conv_r)
+    if method == "spg":
+        _assert_fit_matches_oracle(oracle, d, got, conv, "cluster kernel")
+        assert abs(int(nfe.sum()) - int(nfe_r.sum())) <= 0.1 * nfe_r.sum()
+    else:
+        # Brent under the sweep kernel and under the cluster kernel: the bounded arg-max of the oracle
+        for res in (ref, got):
+            for g in range(0, 96, 5):
+                if d["X"][g].sum() == 0:
+                    continue
+                xb, fb = oracle.brent_gene_1d(d["mu0"][g], d["X"][g], d["beta"], d["lo"], d["hi"], xatol=1e-10)
+                fg = oracle.MarginalF_NB_1D(res[g], d["mu0"][g], d["X"][g], d["beta"])
+                assert fg >= fb - 1e-9 * abs(fb)
+                assert abs(res[g] - xb) <= 1e-5 * xb + 1e-7 or abs(fg - fb) <= 1e-10 * abs(fb)
+        assert rel_err(got, ref).max() <= 1e-5      # Brent brackets the arg-max: no finite-difference jitter
+
+
+def test_fit_gene_without_entries_but_positive_mean(bn, ctx, oracle, small):
+    """BB_Fun takes a caller-supplied INITIAL_MU_vec: a gene with no stored entry and mu > 0 has the likelihood
+    -phi sum log1p(mu beta_j / phi), which is not flat (it decreases in phi) -- BB::spg walks to the lower bound."""
+    X = small["X"][:40].copy()
+    X[5, :] = 0
+    X[17, :] = 0
+    beta = small["beta"]
+    Mo = oracle.CSC.from_dense(X)
+    mu0 = np.maximum(X.sum(1) / beta.sum(), 0.0)
+    mu0[5] = 0.7                      # all-zero row, positive mean
+    s0 = np.full(40, 1.3)
+    lo, hi = 0.05, 9.0
+    want, conv_o, _ = oracle.BB_Fun(Mo, beta, mu0, s0, lo, hi, want_counts=True)
+    got, conv, nfe = bn.BB_Fun(bn.Check_input(X, ctx), beta, mu0, s0, SIZE_lower=lo, SIZE_upper=hi, return_info=True)
+    assert got[17] == 1.3 and nfe[17] == 2                 # mean 0: flat, the start is returned
+    # decreasing in phi: both end on the lower bound (up to the rounding of par + alpha * d in spg's last step)
+    assert abs(want[5] - lo) <= 1e-15 and abs(got[5] - lo) <= 1e-15 and conv[5] == conv_o[5] and nfe[5] > 2
+    assert np.median(rel_err(got, want)) < 1e-6
+
+
 def test_fit_brent_is_argmax(bn, ctx, oracle, small):
     X, beta = small["X"], small["beta"]
     Mo, mu0, s0, lo, hi, want, got, *_ = _fit_case(bn, ctx, oracle, X, beta)
