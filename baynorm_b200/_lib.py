@@ -38,6 +38,7 @@ class PriorOut(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p)
+TILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/baynorm_b200.h declares
 _VP, _I64, _I32, _D, _U64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64
@@ -85,6 +86,13 @@ SIGNATURES = {
     "bn_synthetic_control": (C.c_int, [_VP, _VP, _VP, _U64, _VP, _VP]),
     "bn_beta_fun": (C.c_int, [_VP, _VP, _D, _VP, _VP, _VP]),
     "bn_debug_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "bn_mme_raw": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bn_post_mean_csc": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, C.POINTER(_VP)]),
+    "bn_csc_result_info": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "bn_csc_result_fetch": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bn_csc_result_to_mat": (C.c_int, [_VP, _VP, C.POINTER(_VP)]),
+    "bn_csc_result_free": (None, [_VP]),
+    "bn_post_stream": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _U64, _I64, TILE_SINK, _VP]),
     "bn_debug_last_fit": (C.c_int, [_VP, C.POINTER(_I64)]),
     "bn_debug_tune": (C.c_int, [_VP, C.c_int, C.c_int]),
     "bn_debug_write_peak": (C.c_int, [_VP, _I64, C.c_int, C.c_int, C.POINTER(C.c_double)]),

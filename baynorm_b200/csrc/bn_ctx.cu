@@ -57,6 +57,11 @@ int bn_ctx_create(int device, bn_ctx **out)
         return bn_fail(nullptr, BN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2; k++) {
+        cudaEventCreateWithFlags(&c->ev_comp[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming);
+    }
     cudaHostAlloc((void **)&c->pinned, 64 * sizeof(double), cudaHostAllocDefault);
     c->fit_parked = reinterpret_cast<unsigned int *>(c->pinned + 40);
     *c->fit_parked = 0;
@@ -78,6 +83,15 @@ void bn_ctx_destroy(bn_ctx *ctx)
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+        if (ctx->ev_copy[k]) cudaEventDestroy(ctx->ev_copy[k]);
+        if (ctx->host_tile[k]) cudaFreeHost(ctx->host_tile[k]);
+    }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (void *p : ctx->scratch)
         if (p) cudaFree(p);

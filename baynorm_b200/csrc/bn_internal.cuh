@@ -25,11 +25,16 @@ struct bn_ctx {
     int rank = 0, world = 1;
     cudaEvent_t ev[8] = {};
     double *pinned = nullptr; // 64 doubles of page-locked host memory for truly asynchronous scalar read-backs
-    // grow-only device scratch kept across calls (slots 0-1: the 3-D sampler's element lists; 2-4: pack / key /
-    // sort buffers of the gene-major build): re-allocating GB-sized buffers per call through the stream-ordered
+    // grow-only device scratch kept across calls (slots 0-1, 8-9: the 3-D sampler's lists and side buffers; 2-4: counters of the
+    // gene-major build; 5: DownSampling's list; 6-7: result tiles): re-allocating GB-sized buffers per call through the stream-ordered
     // pool was measured to stall the host for 5-400 ms every few calls
-    void *scratch[8] = {};
-    size_t scratch_bytes[8] = {};
+    void *scratch[12] = {};
+    size_t scratch_bytes[12] = {};
+    // result streaming (bn_stream.cu): a second stream for device -> host copies, two result tiles in flight
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_comp[2] = {}, ev_copy[2] = {};
+    double *host_tile[2] = {};      // pinned, grow-only
+    size_t host_tile_bytes = 0;
     int tune[BN_TUNE_COUNT] = {};   // bn_debug_tune: A/B switches of profiling runs (0 = default)
     int64_t last_fit[4] = {};       // bn_debug_last_fit
     unsigned int *fit_parked = nullptr; // pinned: genes parked by the last sweep kernel
@@ -193,6 +198,13 @@ template <typename T> struct DevOut {
 };
 
 int bn_sync(bn_ctx *ctx);
+// posterior kernels on device pointers, queued on the context's stream without a final synchronisation
+// (kind: 0 mean, 1 mode, 2 S draws); out is G x ncol (x S, planes G*ncol apart)
+int bn_post_device(bn_ctx *ctx, int kind, const bn_mat *m, const double *d_beta, const double *d_size, const double *d_mu,
+                   int64_t col0, int64_t ncol, int S, uint64_t seed, double *d_out);
+// the same for a HOST destination: column tiles, tile t+1 computed while tile t travels (bn_stream.cu)
+int bn_post_to_host(bn_ctx *ctx, int kind, const bn_mat *m, const double *d_beta, const double *d_size, const double *d_mu,
+                    int64_t col0, int64_t ncol, int S, uint64_t seed, double *h_out);
 int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m);
 int bn_mat_ensure_blockptr(bn_ctx *ctx, const bn_mat *m);
 // in-place all-reduce over shards through the user hook (no-op when world == 1)

@@ -285,6 +285,11 @@ extern "C" int bn_mme(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, do
     return bn_mme_impl(ctx, m, 0, beta, MU, SIZE, V);
 }
 
+extern "C" int bn_mme_raw(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, double *SIZE, double *V)
+{
+    return bn_mme_impl(ctx, m, 3, beta, MU, SIZE, V);
+}
+
 extern "C" int bn_row_means(bn_ctx *ctx, bn_mat *m, double *means)
 {
     if (!ctx || !m || !means) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_row_means: NULL argument") : BN_ERR_INVALID;

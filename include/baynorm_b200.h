@@ -124,6 +124,9 @@ BN_API int bn_beta_default(bn_ctx *ctx, const bn_mat *m, double mean_beta, doubl
  * beta[C]: the x/beta normalisation of R/PRIOR_FUNCTIONS.R:253 is then fused in.
  * MU[G], SIZE[G] (NaN where v <= m, i.e. after the rule at :163), V[G]; any may be NULL. */
 BN_API int bn_mme(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, double *SIZE, double *V);
+/* As bn_mme, but SIZE is the raw quotient m^2 / (v - m) that EstPrior_sprcpp itself returns (src/bayNorm_main.cpp:1386);
+ * the NaN rule is applied by R's EstPrior afterwards (R/PRIOR_FUNCTIONS.R:163). */
+BN_API int bn_mme_raw(bn_ctx *ctx, bn_mat *m, const double *beta, double *MU, double *SIZE, double *V);
 /* rowMeansFast / rowVarsFast as separate calls (registered .Call routines). */
 BN_API int bn_row_means(bn_ctx *ctx, bn_mat *m, double *means);
 BN_API int bn_row_vars(bn_ctx *ctx, bn_mat *m, const double *means, double *vars);
@@ -216,6 +219,31 @@ BN_API int bn_post_mode(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, co
  * (tests/testthat/test-bayNorm.r:9-17). */
 BN_API int bn_post_sample(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
                           int64_t col0, int64_t ncol, int S, uint64_t seed, double *out);
+
+/* Sparse result (Main_mean_NB_spBay, src/bayNorm_main.cpp:1519-1601; out.sparse = TRUE, R/bayNorm.r:140-150): the
+ * posterior mean of columns [col0, col0+ncol) as a device-resident CSC matrix holding every non-zero value -- what
+ * `arma::sp_mat(dense)` keeps at :1598 -- without a dense G x C array on the host.  The handle owns device memory. */
+typedef struct bn_csc_result bn_csc_result;
+BN_API int bn_post_mean_csc(bn_ctx *ctx, const bn_mat *m, const double *BETA_vec, const double *size, const double *mu,
+                            int64_t col0, int64_t ncol, bn_csc_result **out);
+/* out[0] = G, [1] = ncol, [2] = nnz */
+BN_API int bn_csc_result_info(const bn_csc_result *r, int64_t out[3]);
+/* Copy the arrays out (host or device destinations; any pointer may be NULL): p64[ncol+1] and/or p32[ncol+1] (R's @p;
+ * fails with BN_ERR_UNSUPPORTED when nnz > 2^31 - 1), i[nnz] 0-based rows, x[nnz]. */
+BN_API int bn_csc_result_fetch(bn_ctx *ctx, const bn_csc_result *r, int64_t *p64, int32_t *p32, int32_t *i, double *x);
+/* The result as a new matrix handle (stays on the device: e.g. the posterior mean fed to another stage). */
+BN_API int bn_csc_result_to_mat(bn_ctx *ctx, bn_csc_result *r, bn_mat **out);
+BN_API void bn_csc_result_free(bn_csc_result *r);
+
+/* Column-block iterator: results larger than device or host memory (configs 3-5: 26 GB - 6.9 TB) stream through
+ * caller-owned host tiles.  kind: 0 mean, 1 mode, 2 S draws.  The library picks the tile width (tile_cols = 0: about
+ * 256 MB of result per tile), computes tile t+1 while tile t is copied to the host on a second stream, and calls
+ * sink(user, col0, ncol, tile) from the calling thread once a tile is complete; `tile` is G x ncol (x S, planes
+ * G*ncol apart) column-major pinned host memory owned by the library, valid until sink returns (write it to disk,
+ * copy it into an R array, ...).  A non-zero return from sink stops the iteration (BN_ERR_INVALID). */
+typedef int (*bn_tile_sink)(void *user, int64_t col0, int64_t ncol, const double *tile);
+BN_API int bn_post_stream(bn_ctx *ctx, const bn_mat *m, int kind, const double *BETA_vec, const double *size,
+                          const double *mu, int S, uint64_t seed, int64_t tile_cols, bn_tile_sink sink, void *user);
 
 /* ---- DownSampling  (src/bayNorm_main.cpp:892-915) ---------------------------------- */
 /* Dense column-major in/out; out[i,j] ~ Binomial(Data[i,j], BETA_vec[j]). */

@@ -1,5 +1,4 @@
-/* Declarations-only stand-ins for the R headers (no R in this image): just enough of the API that r_shim/ uses for a
- * `gcc -fsyntax-only` check of the shim against include/baynorm_b200.h.  Not the real headers, never linked. */
+/* Stand-in for R_ext/Rdynload.h: see R.h in this directory. */
 #pragma once
 typedef void *(*DL_FUNC)(void);
 typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;

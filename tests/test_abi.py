@@ -80,12 +80,12 @@ def test_argument_errors_are_raised_before_any_gpu_work():
 
 def test_r_shim_matches_the_c_abi():
     """r_shim/baynorm_b200_shim.c cannot be built here (no R), but it can be type-checked: declarations-only stand-ins
-    for R.h / Rinternals.h (tests/rstub/) plus the real include/baynorm_b200.h.  Any call of a bn_* entry point with
+    for R.h / Rinternals.h (tests/rmock/) plus the real include/baynorm_b200.h.  Any call of a bn_* entry point with
     the wrong arity or pointer types, or a registered routine with the wrong argument count, fails here."""
     import subprocess
     src = ROOT / "r_shim" / "baynorm_b200_shim.c"
     r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
-                        "-Werror=int-conversion", "-I", str(ROOT / "tests" / "rstub"), "-I", str(ROOT / "include"), str(src)],
+                        "-Werror=int-conversion", "-I", str(ROOT / "tests" / "rmock"), "-I", str(ROOT / "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     text = src.read_text()
@@ -94,10 +94,12 @@ def test_r_shim_matches_the_c_abi():
         m = re.search(r"SEXP %s\(([^)]*)\)" % name, text)
         assert m, name
         assert m.group(1).count("SEXP") == int(arity), (name, arity, m.group(1))
-    # the reference's 15 registered names that sit on the path keep their arities (src/RcppExports.cpp:211-228)
+    # ALL 15 names the reference registers keep their arities (src/RcppExports.cpp:211-228)
     want = {"_bayNorm_DownSampling": 2, "_bayNorm_MarginalF_NB_1D": 4, "_bayNorm_MarginalF_NB_2D": 3, "_bayNorm_GradientFun_NB_1D": 4,
             "_bayNorm_GradientFun_NB_2D": 3, "_bayNorm_Main_NB_Bay": 6, "_bayNorm_Main_mean_NB_Bay": 6, "_bayNorm_Main_mode_NB_Bay": 6,
-            "_bayNorm_rowMeansFast": 1, "_bayNorm_rowVarsFast": 2, "_bayNorm_EstPrior_sprcpp": 1, "_bayNorm_EstPrior_rcpp": 1}
+            "_bayNorm_rowMeansFast": 1, "_bayNorm_rowVarsFast": 2, "_bayNorm_EstPrior_sprcpp": 1, "_bayNorm_EstPrior_rcpp": 1,
+            "_bayNorm_t_sp": 1, "_bayNorm_asMatrix": 5, "_bayNorm_Main_mean_NB_spBay": 6}
+    assert len(want) == 15
     got = dict((n, int(a)) for n, a in re.findall(r'\{"(\w+)", \(DL_FUNC\)&\w+, (\d+)\}', text))
     for n, a in want.items():
         assert got.get(n) == a, (n, got.get(n))
