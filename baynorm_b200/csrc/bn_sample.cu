@@ -37,7 +37,6 @@
 #define SM_NCMAX 64   // columns walked by one CTA
 #define SM_KMAX 512   // table points beyond which an element goes to the gamma-Poisson list
 #define SM_HBLOCK 64  // deferred-list slots a warp reserves per global atomic
-#define HZ_PLANES 32  // planes a k_hz_sample CTA stages per pass (a multiple of 8)
 #define SM_TOPF 4293918720.0f // (1 - 2^-12) * 2^32: a table holding this much mass is "complete"
 #define SM_LIGHT_MASS 0.85f   // mass 32 points must hold (at the gene's largest mean) for its x = 0 elements to stay in the main kernel
 #define SM_LIGHT_MAX 30.0f    // ... and that mean must stay below this
@@ -239,48 +238,80 @@ template <int KT, int STRIDE> struct NbTable {
 // list order is deterministic) and sampling.
 // ---------------------------------------------------------------------------------
 struct NzItem {
-    uint32_t krel; // position in the CSC arrays relative to the chunk's first entry
+    uint32_t krel; // stored entry: position in the CSC arrays relative to the chunk's first entry;
+                   // x = 0 element of a heavy gene: NZ_PAIR | row of the gene in the byte side buffer
     int32_t col;   // column relative to the chunk
 };
+#define NZ_PAIR 0x80000000u
 
-// Thread per stored entry, NZC_PER_CTA entries per CTA.  FILL = false: cnt[c * ncta + cta] = entries of class c this CTA saw.
-// FILL = true: cnt holds the list position of the CTA's first entry of class c (k_nz_offsets); the entries take the next
-// slots in whatever order the shared-memory counters hand out -- the list order only decides which thread draws an entry.
+// Thread per element, NZC_PER_CTA elements per CTA: the nnz stored entries of the chunk, then the nheavy x ncol (heavy gene,
+// column) pairs -- the x = 0 elements of genes the main kernel does not draw; a pair that turns out to be a stored entry
+// (looked up in the column's slice of the gene's row block) is dropped.  Every element is classified on its own: most columns
+// of a heavy gene need far fewer points than its worst column.
+// FILL = false: cnt[c * ncta + cta] = elements of class c this CTA saw.  FILL = true: cnt holds the list position of the
+// CTA's first element of class c (k_nz_offsets); the elements take the next slots in whatever order the shared-memory
+// counters hand out -- the list order only decides which thread draws an element.
 #define NZC_PER_CTA 2048
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_nz_classify(int64_t ncol, int64_t col0, int64_t ncta, const int64_t *__restrict__ colptr,
-                                                     const int32_t *__restrict__ rowidx, const double *__restrict__ val,
-                                                     const double *__restrict__ beta, const double *__restrict__ size,
-                                                     const double *__restrict__ mu, unsigned int *__restrict__ cnt,
+__global__ void __launch_bounds__(256) k_nz_classify(int64_t ncol, int64_t col0, int64_t ncta, int64_t nheavy, const int32_t *__restrict__ hgenes,
+                                                     const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                     const double *__restrict__ val, const double *__restrict__ beta,
+                                                     const double *__restrict__ size, const double *__restrict__ mu,
+                                                     const uint32_t *__restrict__ blockptr, int64_t Ctot, unsigned int *__restrict__ cnt,
                                                      NzItem *__restrict__ list)
 {
     __shared__ unsigned int s_cnt[NB_CLASSES];
-    const int64_t kfirst = __ldg(colptr + col0), klast = __ldg(colptr + col0 + ncol);
+    const int64_t kfirst = __ldg(colptr + col0), nnz = __ldg(colptr + col0 + ncol) - kfirst, nall = nnz + nheavy * ncol;
     if (threadIdx.x < NB_CLASSES) s_cnt[threadIdx.x] = FILL ? cnt[threadIdx.x * ncta + blockIdx.x] : 0u;
     __syncthreads();
-    const int64_t kb = kfirst + (int64_t)blockIdx.x * NZC_PER_CTA;
+    const int64_t vb = (int64_t)blockIdx.x * NZC_PER_CTA;
 #pragma unroll 2
     for (int t = threadIdx.x; t < NZC_PER_CTA; t += 256) {
-        const int64_t k = kb + t;
-        if (k >= klast) break;
-        // column of entry k: last jl with colptr[col0 + jl] <= k
-        int64_t lo = 0, hi = ncol;
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(colptr + col0 + mid) <= k) lo = mid;
-            else hi = mid;
-        }
-        const int32_t i = __ldg(rowidx + k);
-        float rf, Mf;
-        nb_params(__ldg(val + k), (float)__ldg(size + i), (float)__ldg(mu + i), (float)__ldg(beta + col0 + lo), rf, Mf);
-        const int cls = nb_class(rf, Mf);
-        const unsigned slot = atomicAdd(&s_cnt[cls], 1u);
-        if (FILL) {
-            NzItem it;
-            it.krel = (uint32_t)(k - kfirst);
+        const int64_t v = vb + t;
+        if (v >= nall) break;
+        NzItem it;
+        int32_t i;
+        double xv = 0.0;
+        if (v < nnz) {
+            const int64_t k = kfirst + v;
+            // column of entry k: last jl with colptr[col0 + jl] <= k
+            int64_t lo = 0, hi = ncol;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(colptr + col0 + mid) <= k) lo = mid;
+                else hi = mid;
+            }
+            i = __ldg(rowidx + k);
+            xv = __ldg(val + k);
+            it.krel = (uint32_t)v;
             it.col = (int32_t)lo;
-            list[slot] = it;
+        } else {
+            const int64_t pr = v - nnz, h = pr / ncol;
+            i = __ldg(hgenes + h);
+            it.krel = NZ_PAIR | (uint32_t)h;
+            it.col = (int32_t)(pr - h * ncol);
+            // stored? the column's entries of the gene's 128-row block are a run of ~10 sorted row indices
+            const int64_t j = col0 + it.col, cs = __ldg(colptr + j);
+            const uint32_t *bp = blockptr + (int64_t)(i / BN_ROWBLOCK) * Ctot + j;
+            bool stored = false;
+            for (int64_t k = cs + __ldg(bp), ke = cs + __ldg(bp + Ctot); k < ke; k++) {
+                const int32_t r = __ldg(rowidx + k);
+                if (r >= i) {
+                    stored = r == i;
+                    break;
+                }
+            }
+            if (stored) continue;
         }
+        float rf, Mf;
+        nb_params(xv, (float)__ldg(size + i), (float)__ldg(mu + i), (float)__ldg(beta + col0 + it.col), rf, Mf);
+        int cls = nb_class(rf, Mf);
+        // a pair is always drawn here (the gamma-Poisson list is for stored entries and for genes the main kernel owns): the
+        // estimate is a fitted curve, not a monotone bound, so an element may come out above its gene's class -- the 512-point
+        // table then simply sends more words down the recurrence
+        if (v >= nnz && cls == NB_CLASSES - 1) cls = NB_CLASSES - 2;
+        const unsigned slot = atomicAdd(&s_cnt[cls], 1u);
+        if (FILL) list[slot] = it;
     }
     if (!FILL) {
         __syncthreads();
@@ -324,46 +355,62 @@ __global__ void __launch_bounds__(1024) k_nz_offsets(int64_t n /* = NB_CLASSES *
 
 template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_nz_sample(int cls, const NzItem *__restrict__ list,
-                                                       const unsigned long long *__restrict__ offsets, int64_t col0,
+                                                       const unsigned long long *__restrict__ offsets, int64_t G, int64_t ncol, int64_t col0,
                                                        const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                                                       const double *__restrict__ val, const double *__restrict__ beta,
-                                                       const double *__restrict__ size, const double *__restrict__ mu, int S,
-                                                       const __grid_constant__ PhiloxKeys keys, int64_t gene0, int64_t cell0,
-                                                       uint16_t *__restrict__ side)
+                                                       const double *__restrict__ val, const int32_t *__restrict__ hgenes,
+                                                       const double *__restrict__ beta, const double *__restrict__ size,
+                                                       const double *__restrict__ mu, int S, const __grid_constant__ PhiloxKeys keys,
+                                                       int64_t gene0, int64_t cell0, uint8_t *__restrict__ side,
+                                                       uint8_t *__restrict__ sideb, double *__restrict__ out, int64_t sstride)
 {
     extern __shared__ uint32_t nz_tab[]; // [KT][THREADS]
     const uint32_t tsa = (uint32_t)__cvta_generic_to_shared(nz_tab + threadIdx.x);
     const int64_t kfirst = __ldg(colptr + col0);
     const unsigned long long lo = offsets[cls], hi = offsets[cls + 1];
+    const bool vec = (S & 3) == 0; // four draws (one Philox block) leave as one store: single uint16 / byte stores were bound by
+                                   // the store transaction rate, not by the sampling
     for (unsigned long long t = lo + blockIdx.x * (unsigned long long)THREADS + threadIdx.x; t < hi;
          t += (unsigned long long)gridDim.x * THREADS) {
         const NzItem it = list[t];
-        const int64_t k = kfirst + it.krel, j = col0 + it.col;
-        const int32_t i = __ldg(rowidx + k);
-        float rf, Mf;
-        nb_params(__ldg(val + k), (float)__ldg(size + i), (float)__ldg(mu + i), (float)__ldg(beta + j), rf, Mf);
-        uint16_t *o = side + (size_t)it.krel * (size_t)S;
-        if (!(Mf > 0.0f)) { // rgamma(shape, scale = 0) = 0 -> rpois(0) = 0: the draw is x itself
-            for (int s = 0; s < S; s++) o[s] = 0;
-            continue;
+        const bool pair = (it.krel & NZ_PAIR) != 0u;
+        const int64_t j = col0 + it.col;
+        int32_t i;
+        double xv = 0.0;
+        if (pair) i = __ldg(hgenes + (it.krel & ~NZ_PAIR));
+        else {
+            i = __ldg(rowidx + kfirst + it.krel);
+            xv = __ldg(val + kfirst + it.krel);
         }
-        // four draws (one Philox block) leave as one 8-byte store when the entry's run is 8-byte aligned (S % 4 == 0):
-        // single uint16 stores were bound by the store transaction rate, not by the sampling
-        const bool vec = (S & 3) == 0;
-        unsigned long long pack = 0;
+        float rf, Mf;
+        nb_params(xv, (float)__ldg(size + i), (float)__ldg(mu + i), (float)__ldg(beta + j), rf, Mf);
         NbTable<KT, THREADS * 4> T;
-        T.build(tsa, rf, Mf);
-        T.draws(keys, (uint32_t)(gene0 + i), (uint32_t)(cell0 + j), 0, S, [&](int s, uint32_t kv) {
-            const unsigned long long v16 = kv < 65535u ? kv : 65534u;
-            if (vec) {
-                pack |= v16 << (16 * (s & 3));
-                if ((s & 3) == 3) {
-                    *reinterpret_cast<unsigned long long *>(o + (s - 3)) = pack;
-                    pack = 0;
+        const bool table = Mf > 0.0f; // else rgamma(shape, scale = 0) = 0 -> rpois(0) = 0: the draw is x itself
+        if (table) T.build(tsa, rf, Mf);
+        {
+            // bytes for the main kernel's strip -- in CSC order for a stored entry, at (row of the heavy gene, column) for a
+            // pair -- and values >= 255 straight to the output
+            uint8_t *o = pair ? sideb + ((size_t)(it.krel & ~NZ_PAIR) * (size_t)ncol + (size_t)it.col) * (size_t)S
+                              : side + (size_t)it.krel * (size_t)S;
+            double *po = out + i + G * (int64_t)it.col;
+            uint32_t pack = 0;
+            auto emit = [&](int s, uint32_t kv) {
+                if (kv >= 255u) {
+                    __stcs(po + sstride * s, xv + (double)kv);
+                    kv = 255u;
                 }
-            } else
-                o[s] = (uint16_t)v16;
-        });
+                if (vec) {
+                    pack |= kv << (8 * (s & 3));
+                    if ((s & 3) == 3) {
+                        *reinterpret_cast<uint32_t *>(o + (s - 3)) = pack;
+                        pack = 0;
+                    }
+                } else
+                    o[s] = (uint8_t)kv;
+            };
+            if (table) T.draws(keys, (uint32_t)(gene0 + i), (uint32_t)(cell0 + j), 0, S, emit);
+            else
+                for (int s = 0; s < S; s++) emit(s, 0u);
+        }
     }
 }
 
@@ -372,7 +419,7 @@ __global__ void __launch_bounds__(256) k_nz_defer(const NzItem *__restrict__ lis
                                                   int64_t col0, const int64_t *__restrict__ colptr,
                                                   const int32_t *__restrict__ rowidx, const double *__restrict__ val,
                                                   const double *__restrict__ beta, const double *__restrict__ size,
-                                                  const double *__restrict__ mu, int S, uint16_t *__restrict__ side,
+                                                  const double *__restrict__ mu, int S, uint8_t *__restrict__ side,
                                                   HeavyItem *__restrict__ hlist, unsigned int *__restrict__ hcount, unsigned int hcap)
 {
     const int64_t kfirst = __ldg(colptr + col0);
@@ -386,8 +433,8 @@ __global__ void __launch_bounds__(256) k_nz_defer(const NzItem *__restrict__ lis
         h.col = it.col;
         h.x = __ldg(val + k);
         nb_params(h.x, (float)__ldg(size + i), (float)__ldg(mu + i), (float)__ldg(beta + j), h.r, h.M);
-        uint16_t *o = side + (size_t)it.krel * (size_t)S;
-        for (int s = 0; s < S; s++) o[s] = 65535;
+        uint8_t *o = side + (size_t)it.krel * (size_t)S;
+        for (int s = 0; s < S; s++) o[s] = 255;
         const unsigned slot = atomicAdd(hcount, 1u);
         if (slot < hcap) hlist[slot] = h; // past the capacity: hcount > hcap tells the host, which repeats the call
     }
@@ -418,8 +465,8 @@ __global__ void __launch_bounds__(1024) k_min_vec(int64_t n, const double *__res
 
 __global__ void __launch_bounds__(256) k_gene_class(int64_t G, const double *__restrict__ size, const double *__restrict__ mu,
                                                     const float *__restrict__ beta_min, uint8_t *__restrict__ gclass,
-                                                    int32_t *__restrict__ hidx, int32_t *__restrict__ hgenes /*[4][G]*/,
-                                                    unsigned int *__restrict__ hcnt /*[0..3] per class, [4] total*/)
+                                                    int32_t *__restrict__ hidx, int32_t *__restrict__ hgenes /*[G]*/,
+                                                    unsigned int *__restrict__ hcnt /*number of heavy genes*/)
 {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -441,69 +488,10 @@ __global__ void __launch_bounds__(256) k_gene_class(int64_t G, const double *__r
     gclass[g] = (uint8_t)c;
     int32_t h = c == NB_CLASSES - 1 ? -2 : -1; // -2: some element of this gene may need the gamma-Poisson list
     if (c >= 1 && c <= 4) {
-        h = (int32_t)atomicAdd(hcnt + 4, 1u);
-        hgenes[(int64_t)(c - 1) * G + atomicAdd(hcnt + (c - 1), 1u)] = (int32_t)g;
+        h = (int32_t)atomicAdd(hcnt, 1u);
+        hgenes[h] = (int32_t)g;
     }
     hidx[g] = h;
-}
-
-// thread per (heavy gene of class cls, column): lanes walk consecutive columns of one gene (same size, similar mean), the
-// draws go to sideb[(hidx * ncol + column) * S + s] as bytes, values >= 255 straight to the output (x = 0 here; if the
-// element turns out to be a stored entry the main kernel overwrites both with the entry's own draws)
-template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_hz_sample(int cls, int64_t G, int64_t ncol, int64_t col0, const int32_t *__restrict__ hgenes,
-                                                       const unsigned int *__restrict__ hcnt, const int32_t *__restrict__ hidx,
-                                                       const double *__restrict__ beta, const double *__restrict__ size,
-                                                       const double *__restrict__ mu, int S, const __grid_constant__ PhiloxKeys keys,
-                                                       int64_t gene0, int64_t cell0, uint8_t *__restrict__ sideb,
-                                                       double *__restrict__ out, int64_t sstride)
-{
-    extern __shared__ uint32_t nz_tab[]; // [KT][THREADS], then the CTA's bytes [THREADS][planes of the pass]
-    const uint32_t tsa = (uint32_t)__cvta_generic_to_shared(nz_tab + threadIdx.x);
-    uint8_t *s_out = reinterpret_cast<uint8_t *>(nz_tab + (size_t)KT * THREADS);
-    const int SP = S < HZ_PLANES ? S : HZ_PLANES; // planes per pass
-    const int64_t ng = hcnt[cls - 1];
-    const int64_t cblocks = (ncol + THREADS - 1) / THREADS, items = ng * cblocks;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const int64_t gl = it / cblocks, j0 = (it - gl * cblocks) * THREADS, jl = j0 + threadIdx.x;
-        const int32_t g = hgenes[(int64_t)(cls - 1) * G + gl];
-        uint8_t *mine = s_out + (size_t)threadIdx.x * (size_t)SP;
-        float rf = 1.0f, Mf = 0.0f;
-        if (jl < ncol) nb_params(0.0, (float)__ldg(size + g), (float)__ldg(mu + g), (float)__ldg(beta + col0 + jl), rf, Mf);
-        // mean 0: k = 0; p(0) out of the float range cannot happen below the class bound (the main kernel defers such elements
-        // itself and never reads these bytes)
-        const bool table = jl < ncol && Mf > 0.0f && !(rf * log1pf(__fdividef(Mf, rf)) > SM_P0_MAXEXP);
-        NbTable<KT, THREADS * 4> T;
-        if (table) T.build(tsa, rf, Mf);
-        double *po = out + g + G * jl;
-        const int64_t ncb = ncol - j0 < THREADS ? ncol - j0 : THREADS; // columns of this block
-        for (int sb = 0; sb < S; sb += SP) {
-            const int nS = S - sb < SP ? S - sb : SP;
-            if (table)
-                T.draws(keys, (uint32_t)(gene0 + g), (uint32_t)(cell0 + col0 + jl), sb, sb + nS, [&](int s, uint32_t kv) {
-                    if (kv >= 255u) {
-                        __stcs(po + sstride * s, (double)kv);
-                        kv = 255u;
-                    }
-                    mine[s - sb] = (uint8_t)kv;
-                });
-            else
-                for (int s = 0; s < nS; s++) mine[s] = 0;
-            __syncthreads();
-            // planes [sb, sb + nS) of the block's columns: nS contiguous bytes per column, S apart
-            uint8_t *dst = sideb + ((size_t)hidx[g] * (size_t)ncol + (size_t)j0) * (size_t)S + sb;
-            if (nS == S && (((uintptr_t)dst | ((size_t)ncb * S)) & 3) == 0) { // one pass: the block's bytes are ONE contiguous run
-                for (size_t q = threadIdx.x; q < (size_t)ncb * S / 4; q += THREADS)
-                    reinterpret_cast<uint32_t *>(dst)[q] = reinterpret_cast<const uint32_t *>(s_out)[q];
-            } else {
-                for (int64_t q = threadIdx.x; q < ncb * nS; q += THREADS) {
-                    const int64_t c = q / nS, s = q - c * nS;
-                    dst[c * S + s] = s_out[c * SP + s];
-                }
-            }
-            __syncthreads();
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -517,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                        const double *__restrict__ val, const double *__restrict__ beta, const double *__restrict__ size,
                        const double *__restrict__ mu, int64_t col0, int64_t ncol, int nc_per_cta, double *__restrict__ out, int S,
                        const __grid_constant__ PhiloxKeys keys, int64_t gene0, int64_t cell0, int64_t sstride,
-                       const uint8_t *__restrict__ perm, const uint16_t *__restrict__ side, const uint8_t *__restrict__ gclass,
+                       const uint8_t *__restrict__ perm, const uint8_t *__restrict__ side, const uint8_t *__restrict__ gclass,
                        const int32_t *__restrict__ hidx, const uint8_t *__restrict__ sideb, HeavyItem *__restrict__ hlist,
                        unsigned int *__restrict__ hcount, unsigned int hcap, const uint32_t *__restrict__ blockptr, int64_t Ctot)
 {
@@ -571,8 +559,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
     // strip bytes of rows past the end of the matrix stay 255 ("not written here") for good: the flush needs no bounds test
     for (int q = lane; q < SM_GENES * SM_STRIDE; q += 32) s_strip[q] = 0xffffffffu;
-    const uint32_t tsa = (uint32_t)__cvta_generic_to_shared(s_tab + lane);   // this thread's table column: entry k at tsa + k * 128
-    const uint32_t ssa = (uint32_t)__cvta_generic_to_shared(s_strip);        // strip word w of gene g at ssa + (g * SM_STRIDE + w) * 4
+    uint32_t tsa = (uint32_t)__cvta_generic_to_shared(s_tab + lane);   // this thread's table column: entry k at tsa + k * 128
+    uint32_t ssa = (uint32_t)__cvta_generic_to_shared(s_strip);        // strip word w of gene g at ssa + (g * SM_STRIDE + w) * 4
+    // opaque to the compiler from here on: it would otherwise re-derive both from %tid / %ctaid inside the draw loop (15
+    // instructions per four draws) instead of holding two registers
+    asm volatile("" : "+r"(tsa), "+r"(ssa));
     unsigned hblock = 0, hused = SM_HBLOCK; // deferred-list block of this warp (warp-uniform)
     // slice of column 0 into registers
     int32_t pr = 0x7fffffff;
@@ -598,25 +589,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     const bool mine = k + lane < kend;
                     if (mine) {
                         const int g = r2 - (int)w0;
-                        if (sb == 0) xt[g] = v2;
-                        const uint16_t *sp = side + (size_t)(k + lane) * (size_t)S + sb;
-                        double *po = out + G * jl + (w0 + g) + sstride * sb;
+                        // an explicitly stored zero is a stored entry like any other (its draws wait in the side buffer): -0.0
+                        // keeps it apart from "absent" below and adds like 0 in the flush
+                        if (sb == 0) xt[g] = (v2 == 0.0) ? -0.0 : v2;
+                        // the entry's draws (k_nz_sample): one byte per plane, 255 = stored elsewhere (value >= 255: written by
+                        // k_nz_sample itself; gamma-Poisson list: written after this kernel)
+                        const uint8_t *sp = side + (size_t)(k + lane) * (size_t)S + sb;
                         const uint32_t sw = ssa + g * (SM_STRIDE * 4);
-                        for (int w = 0; w < nW; w++) {
-                            uint32_t kq[4];
-#pragma unroll
-                            for (int b = 0; b < 4; b++) kq[b] = (w * 4 + b < nS) ? (uint32_t)__ldg(sp + w * 4 + b) : 255u;
-                            uint32_t word = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                uint32_t kv = kq[b];
-                                if (kv >= 255u) {
-                                    if (kv != 65535u && w * 4 + b < nS) __stcs(po + sstride * (w * 4 + b), v2 + (double)kv);
-                                    kv = 255u; // 65535: on the gamma-Poisson list
-                                }
-                                word |= kv << (8 * b);
+                        if ((S & 3) == 0) {
+                            const uint32_t *spw = reinterpret_cast<const uint32_t *>(sp);
+                            for (int w = 0; w < nW; w++) sts_u32(sw + w * 4, __ldg(spw + w));
+                        } else {
+                            for (int w = 0; w < nW; w++) {
+                                uint32_t word = 0;
+                                for (int b = 0; b < 4; b++) word |= (uint32_t)((w * 4 + b < nS) ? __ldg(sp + w * 4 + b) : 255u) << (8 * b);
+                                sts_u32(sw + w * 4, word);
                             }
-                            sts_u32(sw + w * 4, word);
                         }
                     }
                     k += 32;
@@ -656,7 +644,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 go[0] = go[1], go[1] = go[2], go[2] = go[3], go[3] = g;
                 hz[0] = hz[1], hz[1] = hz[2], hz[2] = hz[3], hz[3] = hz_;
                 const int64_t i = w0 + g;
-                const bool zero = (i < G) && xt[g] == 0.0;
+                const bool zero = (i < G) && __double_as_longlong(xt[g]) == 0ll; // absent from the column (+0.0 exactly)
                 const float mbf = m_ * bf;
                 const float rf = s_, Mf = __fdividef(rf * (m_ - mbf), s_ + mbf);
                 const bool pos = Mf > 0.0f;
@@ -894,25 +882,14 @@ struct SampleArgs {
 };
 
 template <int KT, int THREADS>
-static int launch_nz_class(const SampleArgs &a, int cls, int grid, const NzItem *list, const unsigned long long *offsets, int64_t col0,
-                           uint16_t *side)
+static int launch_nz_class(const SampleArgs &a, int cls, int grid, const NzItem *list, const unsigned long long *offsets, int64_t ncol,
+                           int64_t col0, const int32_t *hgenes, uint8_t *side, uint8_t *sideb, double *out, int64_t sstride)
 {
     bn_ctx *ctx = a.ctx;
     const size_t smem = (size_t)KT * THREADS * 4;
     BN_CUDA(ctx, cudaFuncSetAttribute(k_nz_sample<KT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BN_LAUNCH(ctx, (k_nz_sample<KT, THREADS>), grid, THREADS, smem, cls, list, offsets, col0, a.m->colptr, a.m->rowidx, a.m->val, a.b, a.sz, a.mm,
-              a.S, bn_philox_keys(a.seed), a.m->gene0, a.m->cell0, side);
-    return BN_OK;
-}
-template <int KT, int THREADS>
-static int launch_hz_class(const SampleArgs &a, int cls, int grid, int64_t ncol, int64_t col0, const int32_t *hgenes, const unsigned int *hcnt,
-                           const int32_t *hidx, uint8_t *sideb, double *out, int64_t sstride)
-{
-    bn_ctx *ctx = a.ctx;
-    const size_t smem = (size_t)KT * THREADS * 4 + (((size_t)THREADS * (size_t)std::min(a.S, HZ_PLANES) + 15) & ~(size_t)15);
-    BN_CUDA(ctx, cudaFuncSetAttribute(k_hz_sample<KT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BN_LAUNCH(ctx, (k_hz_sample<KT, THREADS>), grid, THREADS, smem, cls, a.m->G, ncol, col0, hgenes, hcnt, hidx, a.b, a.sz, a.mm, a.S,
-              bn_philox_keys(a.seed), a.m->gene0, a.m->cell0, sideb, out, sstride);
+    BN_LAUNCH(ctx, (k_nz_sample<KT, THREADS>), grid, THREADS, smem, cls, list, offsets, a.m->G, ncol, col0, a.m->colptr, a.m->rowidx, a.m->val,
+              hgenes, a.b, a.sz, a.mm, a.S, bn_philox_keys(a.seed), a.m->gene0, a.m->cell0, side, sideb, out, sstride);
     return BN_OK;
 }
 
@@ -927,24 +904,32 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
     const int64_t tiles_s = (G + SW_TG - 1) / SW_TG;
     const SampleArgs A{ctx, m, d_beta, d_size, d_mu, S, seed};
     BN_TRY(bn_mat_ensure_blockptr(ctx, m));
-    // slot order of every 128-gene block (padded to whole blocks)
+    // per call: the smallest BETA of the WHOLE vector (largest posterior mean of every gene: which kernel draws a gene's x = 0
+    // elements must not depend on the column block of the call), the slot order of every 128-gene block (padded to whole
+    // blocks) and the heavy genes
     const int64_t nblk = (G + SM_GENES - 1) / SM_GENES;
     DevBuf<uint8_t> perm, gclass;
     DevBuf<int32_t> hidx, hgenes;
     DevBuf<float> bmin;
+    DevBuf<unsigned int> hc; // {gamma-Poisson list slots of the chunk, max over the chunks, heavy genes}
     BN_TRY(perm.alloc(ctx, (size_t)nblk * SM_GENES));
     BN_TRY(gclass.alloc(ctx, (size_t)G));
     BN_TRY(hidx.alloc(ctx, (size_t)G));
-    BN_TRY(hgenes.alloc(ctx, (size_t)G * 4));
+    BN_TRY(hgenes.alloc(ctx, (size_t)G));
     BN_TRY(bmin.alloc(ctx, 1));
-    // smallest BETA of the WHOLE vector (largest posterior mean of every gene): which kernel draws a gene's x = 0 elements
-    // must not depend on the column block of the call
+    BN_TRY(hc.alloc(ctx, 4));
+    BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 4 * sizeof(unsigned int), ctx->stream));
     BN_LAUNCH(ctx, k_min_vec, 1, 1024, 0, m->C, d_beta, bmin.p);
     BN_LAUNCH(ctx, k_sample_perm, (unsigned)((nblk + 7) / 8), 256, 0, G, d_size, d_mu, bmin.p, perm.p);
-    // column chunks: the side buffers (2 S bytes per stored entry + 8 for its list item; S bytes per (heavy gene, column), with
-    // up to ~1/4 of the genes heavy) stay below ~1 GB
+    BN_LAUNCH(ctx, k_gene_class, (unsigned)((G + 255) / 256), 256, 0, G, d_size, d_mu, bmin.p, gclass.p, hidx.p, hgenes.p, hc.p + 2);
+    unsigned int *h_nh = reinterpret_cast<unsigned int *>(ctx->pinned + 34);
+    BN_CUDA(ctx, cudaMemcpyAsync(h_nh, hc.p + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    BN_TRY(bn_sync(ctx));
+    const int64_t nheavy = (int64_t)*h_nh;
+    // column chunks: the side buffers (2 S bytes per stored entry, S bytes per (heavy gene, column), 8 bytes of list per element of
+    // either kind) stay below ~1 GB
     const double rho = (double)m->nnz / ((double)G * (double)m->C);
-    const double per_col = std::max(1.0, rho * (double)G) * (2.0 * S + 8.0) + 0.25 * (double)G * S;
+    const double per_col = (std::max(1.0, rho * (double)G) + (double)nheavy) * (S + 8.0);
     for (int attempt = 0; attempt < 2; attempt++) {
         const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, (int64_t)(((double)(1 << 30)) / per_col)));
         // capacity of the gamma-Poisson list (whole blocks of SM_HBLOCK): first attempt 1/8 entry per expected non-zero
@@ -955,17 +940,14 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
         const size_t cap = (((size_t)(per_elem * (double)G * (double)chunk) + SM_HBLOCK - 1) / SM_HBLOCK + (size_t)SW_WARPS * max_ctas + 1) * SM_HBLOCK;
         if (cap > 0xfffffff0u) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: element list too long");
         struct { HeavyItem *p; } hl;
-        struct { uint16_t *p; } side;
+        struct { uint8_t *p; } side;
         struct { NzItem *p; } list;
         struct { uint8_t *p; } sideb;
         BN_TRY(bn_ctx_scratch(ctx, 0, cap * sizeof(HeavyItem), (void **)&hl.p));
-        DevBuf<unsigned int> hc;        // {list slots of the chunk, max over the chunks, -, -, heavy genes per class [4], total [1]}
-        DevBuf<unsigned long long> offs; // start of every class in the entry list [7]
-        DevBuf<unsigned int> ccnt;      // per (class, column) counts -> positions
-        BN_TRY(hc.alloc(ctx, 16));
+        DevBuf<unsigned long long> offs; // start of every class in the element list [7]
+        DevBuf<unsigned int> ccnt;      // per (class, CTA) counts -> positions
         BN_TRY(offs.alloc(ctx, 8));
-
-        BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 16 * sizeof(unsigned int), ctx->stream));
+        BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 2 * sizeof(unsigned int), ctx->stream));
         // stored entries per chunk: read the column pointers of the chunk boundaries
         const int64_t nchunk = (ncol + chunk - 1) / chunk;
         std::vector<int64_t> bounds((size_t)nchunk + 1);
@@ -976,41 +958,32 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
         BN_TRY(bn_sync(ctx));
         int64_t max_nnz = 1;
         for (int64_t c = 0; c < nchunk; c++) max_nnz = std::max(max_nnz, bounds[(size_t)c + 1] - bounds[(size_t)c]);
-        if (max_nnz >= 4294967295LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: more than 2^32 stored entries in a column chunk");
-        BN_TRY(bn_ctx_scratch(ctx, 1, (size_t)max_nnz * (size_t)S * 2, (void **)&side.p));
-        BN_TRY(bn_ctx_scratch(ctx, 9, (size_t)max_nnz * sizeof(NzItem), (void **)&list.p));
-        BN_TRY(ccnt.alloc(ctx, (size_t)NB_CLASSES * (size_t)((max_nnz + NZC_PER_CTA - 1) / NZC_PER_CTA + 1)));
+        const int64_t max_all = max_nnz + nheavy * chunk;
+        if (max_all >= 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: more than 2^31 list elements in a column chunk");
+        BN_TRY(bn_ctx_scratch(ctx, 1, (size_t)max_nnz * (size_t)S, (void **)&side.p));
+        BN_TRY(bn_ctx_scratch(ctx, 8, (size_t)std::max<int64_t>(1, nheavy * chunk) * (size_t)S, (void **)&sideb.p));
+        BN_TRY(bn_ctx_scratch(ctx, 9, (size_t)max_all * sizeof(NzItem), (void **)&list.p));
+        BN_TRY(ccnt.alloc(ctx, (size_t)NB_CLASSES * (size_t)((max_all + NZC_PER_CTA - 1) / NZC_PER_CTA + 1)));
         for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
             const int64_t nc_ = std::min<int64_t>(chunk, ncol - c0);
             const int64_t jc = col0 + c0;
             double *o = d_out + G * c0; // addressed relative to the chunk's first column; planes stay G*ncol apart
             const int64_t sstride = G * ncol;
             BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, sizeof(unsigned int), ctx->stream));
-            BN_CUDA(ctx, cudaMemsetAsync(hc.p + 4, 0, 5 * sizeof(unsigned int), ctx->stream));
-            // ---- heavy genes of this chunk: class at the smallest BETA, then their x = 0 draws -------------------------------
-            BN_LAUNCH(ctx, k_gene_class, (unsigned)((G + 255) / 256), 256, 0, G, d_size, d_mu, bmin.p, gclass.p, hidx.p, hgenes.p, hc.p + 4);
-            unsigned int *h_nh = reinterpret_cast<unsigned int *>(ctx->pinned + 34);
-            BN_CUDA(ctx, cudaMemcpyAsync(h_nh, hc.p + 8, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            BN_TRY(bn_sync(ctx));
-            const size_t nheavy = *h_nh;
-            BN_TRY(bn_ctx_scratch(ctx, 8, std::max<size_t>(1, nheavy) * (size_t)nc_ * (size_t)S, (void **)&sideb.p));
-            if (nheavy) {
-                BN_TRY((launch_hz_class<64, 256>(A, 1, sms * 3, nc_, jc, hgenes.p, hc.p + 4, hidx.p, sideb.p, o, sstride)));
-                BN_TRY((launch_hz_class<128, 128>(A, 2, sms * 3, nc_, jc, hgenes.p, hc.p + 4, hidx.p, sideb.p, o, sstride)));
-                BN_TRY((launch_hz_class<256, 128>(A, 3, sms, nc_, jc, hgenes.p, hc.p + 4, hidx.p, sideb.p, o, sstride)));
-                BN_TRY((launch_hz_class<512, 64>(A, 4, sms, nc_, jc, hgenes.p, hc.p + 4, hidx.p, sideb.p, o, sstride)));
-            }
-            // ---- stored entries ----------------------------------------------------------------------------------------
+            // ---- stored entries and the x = 0 elements of heavy genes: classify, then draw class by class -----------------
             const int64_t nnz_c = bounds[(size_t)(c0 / chunk) + 1] - bounds[(size_t)(c0 / chunk)];
-            const int64_t ncta = std::max<int64_t>(1, (nnz_c + NZC_PER_CTA - 1) / NZC_PER_CTA);
-            BN_LAUNCH(ctx, k_nz_classify<false>, (unsigned)ncta, 256, 0, nc_, jc, ncta, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, ccnt.p, list.p);
+            const int64_t nall = nnz_c + nheavy * nc_;
+            const int64_t ncta = std::max<int64_t>(1, (nall + NZC_PER_CTA - 1) / NZC_PER_CTA);
+#define NZC_ARGS nc_, jc, ncta, nheavy, hgenes.p, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, m->blockptr, m->C, ccnt.p, list.p
+            BN_LAUNCH(ctx, k_nz_classify<false>, (unsigned)ncta, 256, 0, NZC_ARGS);
             BN_LAUNCH(ctx, k_nz_offsets, 1, 1024, 0, (int64_t)NB_CLASSES * ncta, ncta, ccnt.p, offs.p);
-            BN_LAUNCH(ctx, k_nz_classify<true>, (unsigned)ncta, 256, 0, nc_, jc, ncta, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, ccnt.p, list.p);
-            BN_TRY((launch_nz_class<32, 256>(A, 0, sms * 4, list.p, offs.p, jc, side.p)));
-            BN_TRY((launch_nz_class<64, 256>(A, 1, sms * 3, list.p, offs.p, jc, side.p)));
-            BN_TRY((launch_nz_class<128, 128>(A, 2, sms * 3, list.p, offs.p, jc, side.p)));
-            BN_TRY((launch_nz_class<256, 128>(A, 3, sms, list.p, offs.p, jc, side.p)));
-            BN_TRY((launch_nz_class<512, 64>(A, 4, sms, list.p, offs.p, jc, side.p)));
+            BN_LAUNCH(ctx, k_nz_classify<true>, (unsigned)ncta, 256, 0, NZC_ARGS);
+#undef NZC_ARGS
+            BN_TRY((launch_nz_class<32, 256>(A, 0, sms * 4, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
+            BN_TRY((launch_nz_class<64, 256>(A, 1, sms * 3, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
+            BN_TRY((launch_nz_class<128, 128>(A, 2, sms * 3, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
+            BN_TRY((launch_nz_class<256, 128>(A, 3, sms, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
+            BN_TRY((launch_nz_class<512, 64>(A, 4, sms, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
             BN_LAUNCH(ctx, k_nz_defer, sms, 256, 0, list.p, offs.p, jc, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, S, side.p, hl.p,
                       hc.p, (unsigned)cap);
             // ---- x = 0 elements of light genes, strip, flush --------------------------------------------------------------
