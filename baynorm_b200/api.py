@@ -247,7 +247,10 @@ def Check_input(Data, ctx=None, rownames=None, colnames=None):
     except Exception:  # pragma: no cover
         sp = None
     if sp is not None and sp.issparse(Data):
-        M = Data.tocsc()
+        # never touch the caller's matrix: tocsc() hands back the SAME object when the input already is CSC, and the
+        # canonical form the library wants (no duplicate entries, row indices increasing in a column) is made in place
+        M = Data.tocsc(copy=True) if Data.format == "csc" else Data.tocsc()
+        M.sum_duplicates()
         M.sort_indices()
         G, Cn = M.shape
         return DeviceMatrix.from_csc(ctx, G, Cn, M.indptr, M.indices, M.data, rownames=rownames, colnames=colnames)
@@ -310,10 +313,8 @@ def rowVarsFast(x, means, ctx=None):
 def _mme(M, beta, nan_rule=True):
     MU, SIZE, V = (np.zeros(M.G, _F64) for _ in range(3))
     b = None if beta is None else _vec(beta, M.C, "BETA_vec")
-    M.ctx.check(M.ctx.lib.bn_mme(M.ctx.h, M.h, _ptr(b), _ptr(MU), _ptr(SIZE), _ptr(V)))
-    if not nan_rule:
-        with np.errstate(divide="ignore", invalid="ignore"):
-            SIZE = np.where(np.isnan(SIZE), MU * MU / (V - MU), SIZE)
+    fn = M.ctx.lib.bn_mme if nan_rule else M.ctx.lib.bn_mme_raw     # raw: the quotient m^2 / (v - m) as EstPrior_sprcpp returns it
+    M.ctx.check(fn(M.ctx.h, M.h, _ptr(b), _ptr(MU), _ptr(SIZE), _ptr(V)))
     return MU, SIZE, V
 
 
@@ -379,10 +380,29 @@ def Main_mode_NB_Bay(Data, BETA_vec, size, mu, S=20, thres=None, **kw):
     return _posterior("mode", Data, BETA_vec, size, mu, S, thres, **kw)
 
 
-def Main_mean_NB_spBay(Data, BETA_vec, size, mu, S=20, thres=None, **kw):
-    """src/bayNorm_main.cpp:1519-1601: the dense mean converted to a sparse matrix (:1598)."""
+def Main_mean_NB_spBay(Data, BETA_vec, size, mu, S=20, thres=None, ctx=None, col0=0, ncol=None):
+    """src/bayNorm_main.cpp:1519-1601: the posterior mean as a sparse matrix holding every non-zero value (:1598).  Built on the
+    device (bn_post_mean_csc): no dense G x C array crosses the bus or sits in host memory."""
     import scipy.sparse as sp
-    return sp.csc_matrix(_posterior("mean", Data, BETA_vec, size, mu, S, thres, **kw))
+    M = Check_input(Data, ctx)
+    ctx = M.ctx
+    if mu is None:
+        raise ValueError("mu must be supplied (the reference dereferences it unconditionally, src/bayNorm_main.cpp:1118)")
+    ncol = M.C - col0 if ncol is None else int(ncol)
+    b, sz, m = _vec(BETA_vec, M.C, "BETA_vec"), _vec(size, M.G, "size"), _vec(mu, M.G, "mu")
+    res = C.c_void_p()
+    ctx.check(ctx.lib.bn_post_mean_csc(ctx.h, M.h, _ptr(b), _ptr(sz), _ptr(m), int(col0), ncol, C.byref(res)))
+    try:
+        info = (C.c_int64 * 3)()
+        ctx.check(ctx.lib.bn_csc_result_info(res, info))
+        nnz = int(info[2])
+        p = np.zeros(ncol + 1, np.int64)
+        i = np.zeros(nnz, np.int32)
+        x = np.zeros(nnz, _F64)
+        ctx.check(ctx.lib.bn_csc_result_fetch(ctx.h, res, _ptr(p), None, _ptr(i), _ptr(x)))
+    finally:
+        ctx.lib.bn_csc_result_free(res)
+    return sp.csc_matrix((x, i, p), shape=(M.G, ncol))
 
 
 def DownSampling(Data, BETA_vec, seed=None, ctx=None):
@@ -452,11 +472,15 @@ def _fit_opts(GR=False, method="spg", maxfeval=500, park_after=0):
 def BB_Fun(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec, MU_lower=0.01, MU_upper=500, SIZE_lower=0.01,
            SIZE_upper=30, parallel=False, NCores=5, FIX_MU=True, GR=False, method="spg", ctx=None,
            return_info=False, park_after=0):
-    """R/PRIOR_FUNCTIONS.R:380-549.  `parallel`/`NCores` are accepted and ignored: the fit of
-    all genes is one kernel launch.  FIX_MU=False returns the G x 2 matrix (size, mu) of the
-    reference (:543-546), fitted in the box of its parallel=TRUE branch (:414-419)."""
+    """R/PRIOR_FUNCTIONS.R:380-549.  `NCores` is accepted and ignored: the fit of all genes is one kernel
+    launch.  FIX_MU=False returns the G x 2 matrix (size, mu) of the reference (:543-546).  `parallel` keeps its one
+    visible effect upstream: the parallel=TRUE branch boxes (size, mu) by c(SIZE_lower, MU_lower) .. c(SIZE_upper,
+    MU_upper) (:414-419, :457-470), the parallel=FALSE branch hands spg the scalars SIZE_lower / SIZE_upper (:503-526),
+    which BB::spg recycles over BOTH parameters."""
     M = Check_input(Data, ctx)
     ctx = M.ctx
+    if not FIX_MU and not parallel:
+        MU_lower, MU_upper = SIZE_lower, SIZE_upper
     b, mu0, s0 = _vec(BETA_vec, M.C, "BETA_vec"), _vec(INITIAL_MU_vec, M.G), _vec(INITIAL_SIZE_vec, M.G)
     out = np.zeros(M.G, _F64)
     conv = np.zeros(M.G, np.int32)
@@ -500,8 +524,8 @@ def Prior_fun(Data, BETA_vec, parallel=True, NCores=5, FIX_MU=True, GR=False, BB
         if verbose:
             print("Start optimization using spg from BB package.\nThis part may be time-consuming.")
         par, conv, nfe = BB_Fun(M, b, MU, SIZE, MU_lower=rng[0], MU_upper=rng[1], SIZE_lower=base["_info"]["size_lower"],
-                                SIZE_upper=base["_info"]["size_upper"], FIX_MU=False, GR=GR, method=method, ctx=ctx,
-                                return_info=True)
+                                SIZE_upper=base["_info"]["size_upper"], parallel=parallel, FIX_MU=False, GR=GR, method=method,
+                                ctx=ctx, return_info=True)
         ADJ = AdjustSIZE_fun(np.ascontiguousarray(par[:, 0]), MU, SIZE, ctx=ctx)
         if verbose:
             print("Prior estimation has completed!")

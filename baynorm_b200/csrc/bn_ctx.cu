@@ -150,6 +150,30 @@ int bn_sync(bn_ctx *ctx)
     return BN_OK;
 }
 
+// Gene-sharded runs: every shard must take the same branch before a collective, or the others wait forever in the hook.
+// Returns the largest status code over all shards (one max all-reduce of a double); with world == 1 the local code.
+int bn_agree(bn_ctx *ctx, int local_rc)
+{
+    if (ctx->world <= 1) return local_rc;
+    DevBuf<double> d;
+    if (d.alloc(ctx, 1) != BN_OK) return BN_ERR_OOM;
+    const double v = (double)local_rc;
+    double *h = ctx->pinned + 48;
+    *h = v;
+    if (cudaMemcpyAsync(d.p, h, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return BN_ERR_CUDA;
+    const std::string keep = ctx->err;
+    const int rc = bn_allreduce(ctx, d.p, 1, 2);
+    if (rc != BN_OK) return rc;
+    if (cudaMemcpyAsync(h, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return BN_ERR_CUDA;
+    const int g = (int)*h;
+    if (g != BN_OK && local_rc == BN_OK)
+        bn_fail(ctx, g, "another gene shard failed with status %d (this shard's inputs were fine)", g);
+    else
+        ctx->err = keep;
+    return g;
+}
+
 int bn_allreduce(bn_ctx *ctx, double *dev, int64_t count, int op)
 {
     if (ctx->world <= 1 || count <= 0) return BN_OK;

@@ -207,6 +207,8 @@ int bn_post_to_host(bn_ctx *ctx, int kind, const bn_mat *m, const double *d_beta
                     int64_t col0, int64_t ncol, int S, uint64_t seed, double *h_out);
 int bn_mat_ensure_csr(bn_ctx *ctx, bn_mat *m);
 int bn_mat_ensure_blockptr(bn_ctx *ctx, const bn_mat *m);
+// largest status code over all gene shards (bn_ctx.cu): called before the first collective of an entry point
+int bn_agree(bn_ctx *ctx, int local_rc);
 // in-place all-reduce over shards through the user hook (no-op when world == 1)
 int bn_allreduce(bn_ctx *ctx, double *dev, int64_t count, int op);
 

@@ -20,6 +20,14 @@ extern "C" int bn_prior(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, int BB_S
     if (!ctx || !m || !BETA_vec || !out) return ctx ? bn_fail(ctx, BN_ERR_INVALID, "bn_prior: NULL argument") : BN_ERR_INVALID;
     if (m->C < 2) return bn_fail(ctx, BN_ERR_INVALID, "bn_prior needs at least 2 cells");
     cudaSetDevice(ctx->device);
+    // a shard whose gene block holds a non-count value would leave bn_fit_size_device between the collectives of this call
+    // and strand the other shards in the hook: agree on the verdict first
+    {
+        int rc = (BB_SIZE && !m->is_count) ? BN_ERR_NONCOUNT : BN_OK;
+        if (rc) bn_fail(ctx, rc, "the likelihood fit needs non-negative integer counts (dnbinom_mu is 0 elsewhere)");
+        rc = bn_agree(ctx, rc);
+        if (rc != BN_OK) return rc;
+    }
     const size_t G = (size_t)m->G;
     DevIn<double> beta;
     BN_TRY(beta.bind(ctx, BETA_vec, (size_t)m->C));
