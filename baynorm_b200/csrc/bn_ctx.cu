@@ -62,6 +62,14 @@ int bn_ctx_create(int device, bn_ctx **out)
         cudaEventCreateWithFlags(&c->ev_comp[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming);
     }
+    {
+        // side streams get the highest priority: their short, low-occupancy kernels slot in between the CTAs of the long
+        // kernel on `stream` instead of queueing behind its whole grid
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (auto &st : c->aux) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi);
+    }
+    for (auto &ev : c->ev_aux) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaHostAlloc((void **)&c->pinned, 64 * sizeof(double), cudaHostAllocDefault);
     c->fit_parked = reinterpret_cast<unsigned int *>(c->pinned + 40);
     *c->fit_parked = 0;
@@ -92,6 +100,13 @@ void bn_ctx_destroy(bn_ctx *ctx)
         if (ctx->ev_copy[k]) cudaEventDestroy(ctx->ev_copy[k]);
         if (ctx->host_tile[k]) cudaFreeHost(ctx->host_tile[k]);
     }
+    for (auto &st : ctx->aux)
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    for (auto &ev : ctx->ev_aux)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (void *p : ctx->scratch)
         if (p) cudaFree(p);

@@ -28,8 +28,13 @@ struct bn_ctx {
     // grow-only device scratch kept across calls (slots 0-1, 8-9: the 3-D sampler's lists and side buffers; 2-4: counters of the
     // gene-major build; 5: DownSampling's list; 6-7: result tiles): re-allocating GB-sized buffers per call through the stream-ordered
     // pool was measured to stall the host for 5-400 ms every few calls
-    void *scratch[12] = {};
-    size_t scratch_bytes[12] = {};
+    void *scratch[20] = {};        // slots 10-14: the second set of the 3-D sampler's per-chunk buffers
+    size_t scratch_bytes[20] = {};
+    // side streams of the 3-D sampler (bn_sample.cu): [0] prepares chunk c + 1 (classification, side-buffer draws) while the
+    // main kernel of chunk c runs on `stream`; [1..4] carry the table classes that run next to each other
+    cudaStream_t aux[5] = {};
+    cudaEvent_t ev_aux[12] = {};
+    bool sample_attr_set = false;  // function attributes are per device: set once per context
     // result streaming (bn_stream.cu): a second stream for device -> host copies, two result tiles in flight
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_comp[2] = {}, ev_copy[2] = {};
@@ -94,6 +99,17 @@ int bn_fail(bn_ctx *ctx, int code, const char *fmt, ...);
 #define BN_LAUNCH(ctx, kernel, grid, block, smem, ...)                                          \
     do {                                                                                        \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess)                                                                 \
+            return bn_fail((ctx), BN_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,      \
+                           cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+    } while (0)
+
+// the same on another stream of the context (the side streams of the 3-D sampler)
+#define BN_LAUNCH_ON(ctx, st, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                        \
+        kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                 \
         (ctx)->launches++;                                                                      \
         cudaError_t e__ = cudaGetLastError();                                                   \
         if (e__ != cudaSuccess)                                                                 \

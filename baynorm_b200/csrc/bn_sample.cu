@@ -261,10 +261,23 @@ __global__ void __launch_bounds__(256) k_nz_classify(int64_t ncol, int64_t col0,
                                                      NzItem *__restrict__ list)
 {
     __shared__ unsigned int s_cnt[NB_CLASSES];
+    __shared__ int64_t s_span[2]; // columns (relative to the chunk) of the CTA's first and last stored entry
     const int64_t kfirst = __ldg(colptr + col0), nnz = __ldg(colptr + col0 + ncol) - kfirst, nall = nnz + nheavy * ncol;
     if (threadIdx.x < NB_CLASSES) s_cnt[threadIdx.x] = FILL ? cnt[threadIdx.x * ncta + blockIdx.x] : 0u;
-    __syncthreads();
     const int64_t vb = (int64_t)blockIdx.x * NZC_PER_CTA;
+    if (threadIdx.x < 2 && vb < nnz) {
+        // the CTA's entries are consecutive: their columns lie between those of the first and the last one (two searches per
+        // CTA instead of one 11-step search per entry; a CTA spans one or two columns of a single-cell matrix)
+        const int64_t k = kfirst + (threadIdx.x == 0 ? vb : (vb + NZC_PER_CTA - 1 < nnz ? vb + NZC_PER_CTA - 1 : nnz - 1));
+        int64_t lo = 0, hi = ncol;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(colptr + col0 + mid) <= k) lo = mid;
+            else hi = mid;
+        }
+        s_span[threadIdx.x] = lo;
+    }
+    __syncthreads();
 #pragma unroll 2
     for (int t = threadIdx.x; t < NZC_PER_CTA; t += 256) {
         const int64_t v = vb + t;
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(256) k_nz_classify(int64_t ncol, int64_t col0,
         if (v < nnz) {
             const int64_t k = kfirst + v;
             // column of entry k: last jl with colptr[col0 + jl] <= k
-            int64_t lo = 0, hi = ncol;
+            int64_t lo = s_span[0], hi = s_span[1] + 1;
             while (hi - lo > 1) {
                 const int64_t mid = (lo + hi) >> 1;
                 if (__ldg(colptr + col0 + mid) <= k) lo = mid;
@@ -767,36 +780,34 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             KV = 255u;                                                                                           \
         }                                                                                                        \
     } while (0)
-#define SM_DRAWS(LV)                                                                                             \
-    for (int s0 = 0; s0 < nS; s0 += 4) {                                                                         \
-        uint32_t u0, u1, u2, u3;                                                                                 \
-        bn_philox_block(keys, c0, c1p, (uint32_t)((sb + s0) >> 2), 0u, u0, u1, u2, u3);                          \
-        uint32_t a0 = tsa, a1 = tsa, a2 = tsa, a3 = tsa;                                                         \
-        if (LV >= 6) { SLEVEL(a0, u0, 31, 32); SLEVEL(a1, u1, 31, 32); SLEVEL(a2, u2, 31, 32); SLEVEL(a3, u3, 31, 32); } \
-        if (LV >= 5) { SLEVEL(a0, u0, 15, 16); SLEVEL(a1, u1, 15, 16); SLEVEL(a2, u2, 15, 16); SLEVEL(a3, u3, 15, 16); } \
-        if (LV >= 4) { SLEVEL(a0, u0, 7, 8); SLEVEL(a1, u1, 7, 8); SLEVEL(a2, u2, 7, 8); SLEVEL(a3, u3, 7, 8); }   \
-        SLEVEL(a0, u0, 3, 4); SLEVEL(a1, u1, 3, 4); SLEVEL(a2, u2, 3, 4); SLEVEL(a3, u3, 3, 4);                   \
-        SLEVEL(a0, u0, 1, 2); SLEVEL(a1, u1, 1, 2); SLEVEL(a2, u2, 1, 2); SLEVEL(a3, u3, 1, 2);                   \
-        SLEVEL(a0, u0, 0, 1); SLEVEL(a1, u1, 0, 1); SLEVEL(a2, u2, 0, 1); SLEVEL(a3, u3, 0, 1);                   \
-        uint32_t k0 = SKVAL(a0), k1 = SKVAL(a1), k2 = SKVAL(a2), k3 = SKVAL(a3);                                  \
-        const uint32_t umax = max(max(u0, u1), max(u2, u3));                                                     \
-        if (umax >= tlast) { /* some draw beyond the table (rare): K <= 64 < 255, so inside draws need no check */ \
-            SM_SLOW(k0, u0, s0);                                                                                 \
-            SM_SLOW(k1, u1, s0 + 1);                                                                             \
-            SM_SLOW(k2, u2, s0 + 2);                                                                             \
-            SM_SLOW(k3, u3, s0 + 3);                                                                             \
-        }                                                                                                        \
-        sts_u32(sw + s0, k0 | (k1 << 8) | (k2 << 16) | (k3 << 24));                                              \
-    }
+                // ONE copy of the draw loop; the depth of the search is a warp-uniform run-time value (three uniform branches per
+                // Philox block).  Four specialised copies were 1.3x the instruction-cache footprint (6.8 % of the warp stalls were
+                // "no instruction") and each re-loaded the round keys into its own uniform registers.
                 // (a partial last Philox block -- S not a multiple of 4 -- fills bytes of planes >= nS, which the flush ignores)
                 if (work) {
-                    if (levels == 3) { SM_DRAWS(3) }
-                    else if (levels == 4) { SM_DRAWS(4) }
-                    else if (levels == 5) { SM_DRAWS(5) }
-                    else { SM_DRAWS(LCAP) }
+#pragma unroll 1
+                    for (int s0 = 0; s0 < nS; s0 += 4) {
+                        uint32_t u0, u1, u2, u3;
+                        bn_philox_block(keys, c0, c1p, (uint32_t)((sb + s0) >> 2), 0u, u0, u1, u2, u3);
+                        uint32_t a0 = tsa, a1 = tsa, a2 = tsa, a3 = tsa;
+                        if (LCAP >= 6 && levels >= 6) { SLEVEL(a0, u0, 31, 32); SLEVEL(a1, u1, 31, 32); SLEVEL(a2, u2, 31, 32); SLEVEL(a3, u3, 31, 32); }
+                        if (levels >= 5) { SLEVEL(a0, u0, 15, 16); SLEVEL(a1, u1, 15, 16); SLEVEL(a2, u2, 15, 16); SLEVEL(a3, u3, 15, 16); }
+                        if (levels >= 4) { SLEVEL(a0, u0, 7, 8); SLEVEL(a1, u1, 7, 8); SLEVEL(a2, u2, 7, 8); SLEVEL(a3, u3, 7, 8); }
+                        SLEVEL(a0, u0, 3, 4); SLEVEL(a1, u1, 3, 4); SLEVEL(a2, u2, 3, 4); SLEVEL(a3, u3, 3, 4);
+                        SLEVEL(a0, u0, 1, 2); SLEVEL(a1, u1, 1, 2); SLEVEL(a2, u2, 1, 2); SLEVEL(a3, u3, 1, 2);
+                        SLEVEL(a0, u0, 0, 1); SLEVEL(a1, u1, 0, 1); SLEVEL(a2, u2, 0, 1); SLEVEL(a3, u3, 0, 1);
+                        uint32_t k0 = SKVAL(a0), k1 = SKVAL(a1), k2 = SKVAL(a2), k3 = SKVAL(a3);
+                        const uint32_t umax = max(max(u0, u1), max(u2, u3));
+                        if (umax >= tlast) { /* some draw beyond the table (rare): K <= 64 < 255, so inside draws need no check */
+                            SM_SLOW(k0, u0, s0);
+                            SM_SLOW(k1, u1, s0 + 1);
+                            SM_SLOW(k2, u2, s0 + 2);
+                            SM_SLOW(k3, u3, s0 + 3);
+                        }
+                        sts_u32(sw + s0, k0 | (k1 << 8) | (k2 << 16) | (k3 << 24));
+                    }
                 }
                 __syncwarp();
-#undef SM_DRAWS
 #undef SM_SLOW
 #undef SKVAL
 #undef SLEVEL
@@ -882,14 +893,15 @@ struct SampleArgs {
 };
 
 template <int KT, int THREADS>
-static int launch_nz_class(const SampleArgs &a, int cls, int grid, const NzItem *list, const unsigned long long *offsets, int64_t ncol,
-                           int64_t col0, const int32_t *hgenes, uint8_t *side, uint8_t *sideb, double *out, int64_t sstride)
+static int launch_nz_class(const SampleArgs &a, cudaStream_t st, int cls, int grid, const NzItem *list, const unsigned long long *offsets,
+                           int64_t ncol, int64_t col0, const int32_t *hgenes, uint8_t *side, uint8_t *sideb, double *out, int64_t sstride)
 {
     bn_ctx *ctx = a.ctx;
     const size_t smem = (size_t)KT * THREADS * 4;
     BN_CUDA(ctx, cudaFuncSetAttribute(k_nz_sample<KT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BN_LAUNCH(ctx, (k_nz_sample<KT, THREADS>), grid, THREADS, smem, cls, list, offsets, a.m->G, ncol, col0, a.m->colptr, a.m->rowidx, a.m->val,
-              hgenes, a.b, a.sz, a.mm, a.S, bn_philox_keys(a.seed), a.m->gene0, a.m->cell0, side, sideb, out, sstride);
+    BN_CUDA(ctx, cudaFuncSetAttribute(k_nz_sample<KT, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    BN_LAUNCH_ON(ctx, st, (k_nz_sample<KT, THREADS>), grid, THREADS, smem, cls, list, offsets, a.m->G, ncol, col0, a.m->colptr, a.m->rowidx,
+                 a.m->val, hgenes, a.b, a.sz, a.mm, a.S, bn_philox_keys(a.seed), a.m->gene0, a.m->cell0, side, sideb, out, sstride);
     return BN_OK;
 }
 
@@ -903,6 +915,20 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
     const int64_t SW_TG = (int64_t)SM_GENES * SW_WARPS;
     const int64_t tiles_s = (G + SW_TG - 1) / SW_TG;
     const SampleArgs A{ctx, m, d_beta, d_size, d_mu, S, seed};
+    {
+        // one shared-memory carveout for every kernel of the pipeline: CTAs of kernels that ask for different carveouts cannot
+        // share an SM, which would serialise the side streams behind the main kernel
+        if (!ctx->sample_attr_set) {
+            cudaFuncSetAttribute(k_nz_classify<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_nz_classify<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_nz_offsets, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_nz_defer, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_post_sample_heavy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_post_sample_main<8, 3, 32, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_post_sample_main<8, 3, 32, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            ctx->sample_attr_set = true;
+        }
+    }
     BN_TRY(bn_mat_ensure_blockptr(ctx, m));
     // per call: the smallest BETA of the WHOLE vector (largest posterior mean of every gene: which kernel draws a gene's x = 0
     // elements must not depend on the column block of the call), the slot order of every 128-gene block (padded to whole
@@ -939,14 +965,23 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
         const size_t max_ctas = (size_t)std::max<int64_t>(ctas64, std::min<int64_t>(ctas4, (int64_t)sms * 128 + tiles_s));
         const size_t cap = (((size_t)(per_elem * (double)G * (double)chunk) + SM_HBLOCK - 1) / SM_HBLOCK + (size_t)SW_WARPS * max_ctas + 1) * SM_HBLOCK;
         if (cap > 0xfffffff0u) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: element list too long");
-        struct { HeavyItem *p; } hl;
-        struct { uint8_t *p; } side;
-        struct { NzItem *p; } list;
-        struct { uint8_t *p; } sideb;
-        BN_TRY(bn_ctx_scratch(ctx, 0, cap * sizeof(HeavyItem), (void **)&hl.p));
-        DevBuf<unsigned long long> offs; // start of every class in the element list [7]
-        DevBuf<unsigned int> ccnt;      // per (class, CTA) counts -> positions
-        BN_TRY(offs.alloc(ctx, 8));
+        // Two sets of per-chunk buffers: chunk c + 1 is prepared (classification, side-buffer draws of the stored entries and of the
+        // heavy genes' x = 0 elements) on the side streams while the main kernel of chunk c runs on the context's stream.  The five
+        // table classes are independent launches; the deep ones (128-512 points per thread) hold few warps per SM, so they run
+        // next to each other on their own streams instead of one after the other.
+        struct Set {
+            HeavyItem *hl;
+            uint8_t *side, *sideb;
+            NzItem *list;
+            unsigned int *ccnt;
+            unsigned long long *offs;
+            unsigned int *hcnt; // gamma-Poisson list slots of the chunk
+        } set[2];
+        DevBuf<unsigned long long> offs; // start of every class in the element list [7], two sets
+        DevBuf<unsigned int> ccnt;      // per (class, CTA) counts -> positions, two sets
+        DevBuf<unsigned int> hcs;       // heavy-list counters of the two sets
+        BN_TRY(offs.alloc(ctx, 16));
+        BN_TRY(hcs.alloc(ctx, 2));
         BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, 2 * sizeof(unsigned int), ctx->stream));
         // stored entries per chunk: read the column pointers of the chunk boundaries
         const int64_t nchunk = (ncol + chunk - 1) / chunk;
@@ -960,32 +995,67 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
         for (int64_t c = 0; c < nchunk; c++) max_nnz = std::max(max_nnz, bounds[(size_t)c + 1] - bounds[(size_t)c]);
         const int64_t max_all = max_nnz + nheavy * chunk;
         if (max_all >= 2147483647LL) return bn_fail(ctx, BN_ERR_UNSUPPORTED, "posterior: more than 2^31 list elements in a column chunk");
-        BN_TRY(bn_ctx_scratch(ctx, 1, (size_t)max_nnz * (size_t)S, (void **)&side.p));
-        BN_TRY(bn_ctx_scratch(ctx, 8, (size_t)std::max<int64_t>(1, nheavy * chunk) * (size_t)S, (void **)&sideb.p));
-        BN_TRY(bn_ctx_scratch(ctx, 9, (size_t)max_all * sizeof(NzItem), (void **)&list.p));
-        BN_TRY(ccnt.alloc(ctx, (size_t)NB_CLASSES * (size_t)((max_all + NZC_PER_CTA - 1) / NZC_PER_CTA + 1)));
-        for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
-            const int64_t nc_ = std::min<int64_t>(chunk, ncol - c0);
-            const int64_t jc = col0 + c0;
-            double *o = d_out + G * c0; // addressed relative to the chunk's first column; planes stay G*ncol apart
-            const int64_t sstride = G * ncol;
-            BN_CUDA(ctx, cudaMemsetAsync(hc.p, 0, sizeof(unsigned int), ctx->stream));
-            // ---- stored entries and the x = 0 elements of heavy genes: classify, then draw class by class -----------------
-            const int64_t nnz_c = bounds[(size_t)(c0 / chunk) + 1] - bounds[(size_t)(c0 / chunk)];
+        const size_t ccnt_n = (size_t)NB_CLASSES * (size_t)((max_all + NZC_PER_CTA - 1) / NZC_PER_CTA + 1);
+        BN_TRY(ccnt.alloc(ctx, 2 * ccnt_n));
+        const int nset = nchunk > 1 ? 2 : 1;
+        for (int k = 0; k < nset; k++) {
+            static const int slots[2][4] = {{0, 1, 8, 9}, {10, 11, 12, 13}};
+            BN_TRY(bn_ctx_scratch(ctx, slots[k][0], cap * sizeof(HeavyItem), (void **)&set[k].hl));
+            BN_TRY(bn_ctx_scratch(ctx, slots[k][1], (size_t)max_nnz * (size_t)S, (void **)&set[k].side));
+            BN_TRY(bn_ctx_scratch(ctx, slots[k][2], (size_t)std::max<int64_t>(1, nheavy * chunk) * (size_t)S, (void **)&set[k].sideb));
+            BN_TRY(bn_ctx_scratch(ctx, slots[k][3], (size_t)max_all * sizeof(NzItem), (void **)&set[k].list));
+            set[k].ccnt = ccnt.p + (size_t)k * ccnt_n;
+            set[k].offs = offs.p + 8 * k;
+            set[k].hcnt = hcs.p + k;
+        }
+        if (nset == 1) set[1] = set[0];
+        const int64_t sstride = G * ncol; // planes stay G*ncol apart; a chunk is addressed relative to its first column
+        const bool serial = ctx->tune[BN_TUNE_SAMPLE_SERIAL] == 1;
+        cudaStream_t sp = serial ? ctx->stream : ctx->aux[0];
+        cudaStream_t scl[5] = {sp, serial ? sp : ctx->aux[1], serial ? sp : ctx->aux[2], serial ? sp : ctx->aux[3], serial ? sp : ctx->aux[4]};
+        cudaEvent_t ev_ready = ctx->ev_aux[0];                         // everything queued on the main stream so far (inputs, buffers)
+        cudaEvent_t *ev_prep = ctx->ev_aux + 1, *ev_free = ctx->ev_aux + 3; // [set]: side buffers filled / released by the main kernel
+        cudaEvent_t ev_fork = ctx->ev_aux[5], *ev_cls = ctx->ev_aux + 6;   // class streams
+        BN_CUDA(ctx, cudaEventRecord(ev_ready, ctx->stream));
+        BN_CUDA(ctx, cudaStreamWaitEvent(sp, ev_ready, 0));
+        // prepare chunk c on the side streams
+        auto prepare = [&](int64_t c) -> int {
+            const Set &B = set[c & 1];
+            const int64_t c0 = c * chunk, nc_ = std::min<int64_t>(chunk, ncol - c0), jc = col0 + c0;
+            double *o = d_out + G * c0;
+            if (c >= 2) BN_CUDA(ctx, cudaStreamWaitEvent(sp, ev_free[c & 1], 0)); // the main kernel of chunk c - 2 has read this set
+            BN_CUDA(ctx, cudaMemsetAsync(B.hcnt, 0, sizeof(unsigned int), sp));
+            const int64_t nnz_c = bounds[(size_t)c + 1] - bounds[(size_t)c];
             const int64_t nall = nnz_c + nheavy * nc_;
             const int64_t ncta = std::max<int64_t>(1, (nall + NZC_PER_CTA - 1) / NZC_PER_CTA);
-#define NZC_ARGS nc_, jc, ncta, nheavy, hgenes.p, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, m->blockptr, m->C, ccnt.p, list.p
-            BN_LAUNCH(ctx, k_nz_classify<false>, (unsigned)ncta, 256, 0, NZC_ARGS);
-            BN_LAUNCH(ctx, k_nz_offsets, 1, 1024, 0, (int64_t)NB_CLASSES * ncta, ncta, ccnt.p, offs.p);
-            BN_LAUNCH(ctx, k_nz_classify<true>, (unsigned)ncta, 256, 0, NZC_ARGS);
+#define NZC_ARGS nc_, jc, ncta, nheavy, hgenes.p, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, m->blockptr, m->C, B.ccnt, B.list
+            BN_LAUNCH_ON(ctx, sp, k_nz_classify<false>, (unsigned)ncta, 256, 0, NZC_ARGS);
+            BN_LAUNCH_ON(ctx, sp, k_nz_offsets, 1, 1024, 0, (int64_t)NB_CLASSES * ncta, ncta, B.ccnt, B.offs);
+            BN_LAUNCH_ON(ctx, sp, k_nz_classify<true>, (unsigned)ncta, 256, 0, NZC_ARGS);
 #undef NZC_ARGS
-            BN_TRY((launch_nz_class<32, 256>(A, 0, sms * 4, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
-            BN_TRY((launch_nz_class<64, 256>(A, 1, sms * 3, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
-            BN_TRY((launch_nz_class<128, 128>(A, 2, sms * 3, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
-            BN_TRY((launch_nz_class<256, 128>(A, 3, sms, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
-            BN_TRY((launch_nz_class<512, 64>(A, 4, sms, list.p, offs.p, nc_, jc, hgenes.p, side.p, sideb.p, o, sstride)));
-            BN_LAUNCH(ctx, k_nz_defer, sms, 256, 0, list.p, offs.p, jc, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, S, side.p, hl.p,
-                      hc.p, (unsigned)cap);
+            BN_CUDA(ctx, cudaEventRecord(ev_fork, sp));
+            for (int k = 1; k <= 4; k++) BN_CUDA(ctx, cudaStreamWaitEvent(scl[k], ev_fork, 0));
+            BN_TRY((launch_nz_class<32, 256>(A, sp, 0, sms * 4, B.list, B.offs, nc_, jc, hgenes.p, B.side, B.sideb, o, sstride)));
+            BN_TRY((launch_nz_class<64, 256>(A, scl[1], 1, sms * 3, B.list, B.offs, nc_, jc, hgenes.p, B.side, B.sideb, o, sstride)));
+            BN_TRY((launch_nz_class<128, 128>(A, scl[2], 2, sms * 3, B.list, B.offs, nc_, jc, hgenes.p, B.side, B.sideb, o, sstride)));
+            BN_TRY((launch_nz_class<256, 128>(A, scl[3], 3, sms, B.list, B.offs, nc_, jc, hgenes.p, B.side, B.sideb, o, sstride)));
+            BN_TRY((launch_nz_class<512, 64>(A, scl[4], 4, sms, B.list, B.offs, nc_, jc, hgenes.p, B.side, B.sideb, o, sstride)));
+            BN_LAUNCH_ON(ctx, sp, k_nz_defer, sms, 256, 0, B.list, B.offs, jc, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, S, B.side, B.hl,
+                         B.hcnt, (unsigned)cap);
+            for (int k = 1; k <= 4; k++) {
+                BN_CUDA(ctx, cudaEventRecord(ev_cls[k], scl[k]));
+                BN_CUDA(ctx, cudaStreamWaitEvent(sp, ev_cls[k], 0));
+            }
+            BN_CUDA(ctx, cudaEventRecord(ev_prep[c & 1], sp));
+            return BN_OK;
+        };
+        BN_TRY(prepare(0));
+        for (int64_t c = 0; c < nchunk; c++) {
+            const Set &B = set[c & 1];
+            const int64_t c0 = c * chunk, nc_ = std::min<int64_t>(chunk, ncol - c0), jc = col0 + c0;
+            double *o = d_out + G * c0;
+            if (c + 1 < nchunk) BN_TRY(prepare(c + 1));
+            BN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_prep[c & 1], 0));
             // ---- x = 0 elements of light genes, strip, flush --------------------------------------------------------------
             int ncs = SM_NCMAX; // columns per CTA: short walks keep the columns in flight (and their S planes) close together
             while (ncs > 4 && tiles_s * ((nc_ + ncs - 1) / ncs) < (int64_t)sms * 64) ncs >>= 1;
@@ -995,7 +1065,7 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
             const size_t smem_s = (size_t)SW_WARPS * SM_SMEM_PER_WARP(KCAP);
 #define SM_MAIN_ARGS                                                                                                               \
     G, m->colptr, m->rowidx, m->val, d_beta, d_size, d_mu, jc, nc_, ncs, o, S, bn_philox_keys(seed), m->gene0, m->cell0, sstride, perm.p, \
-        side.p, gclass.p, hidx.p, sideb.p, hl.p, hc.p, (unsigned)cap, m->blockptr, m->C
+        B.side, gclass.p, hidx.p, B.sideb, B.hl, B.hcnt, (unsigned)cap, m->blockptr, m->C
             if (m->is_count) {
                 BN_CUDA(ctx, cudaFuncSetAttribute(k_post_sample_main<SW_WARPS, MINB, KCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
                 BN_LAUNCH(ctx, (k_post_sample_main<SW_WARPS, MINB, KCAP, true>), grid_s, SW_WARPS * 32, smem_s, SM_MAIN_ARGS);
@@ -1005,8 +1075,9 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
             }
 #undef SM_MAIN_ARGS
             // ---- the gamma-Poisson list ---------------------------------------------------------------------------
-            BN_LAUNCH(ctx, k_post_sample_heavy, sms * 8, 256, 0, G, hl.p, hc.p, (unsigned)cap, S, seed, m->gene0, m->cell0, jc, sstride, o,
+            BN_LAUNCH(ctx, k_post_sample_heavy, sms * 8, 256, 0, G, B.hl, B.hcnt, (unsigned)cap, S, seed, m->gene0, m->cell0, jc, sstride, o,
                       hc.p + 1);
+            BN_CUDA(ctx, cudaEventRecord(ev_free[c & 1], ctx->stream));
         }
         unsigned int *h_max = reinterpret_cast<unsigned int *>(ctx->pinned + 32);
         BN_CUDA(ctx, cudaMemcpyAsync(h_max, hc.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));

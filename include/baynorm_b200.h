@@ -284,8 +284,9 @@ BN_API int bn_debug_write_peak(bn_ctx *ctx, int64_t bytes, int planes, int run, 
 BN_API int bn_debug_last_fit(const bn_ctx *ctx, int64_t out[4]);
 /* A/B switches for profiling runs (the product never reads the environment).  value 0 restores the default.
  *   BN_TUNE_FIT_VARIANT   1..3: force that fit kernel variant for long genes (see bn_debug_last_fit)
- *   BN_TUNE_SAMPLE_NCS    columns walked per CTA by the 3-D sampler */
-enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_COUNT = 8 };
+ *   BN_TUNE_SAMPLE_NCS    columns walked per CTA by the 3-D sampler
+ *   BN_TUNE_SAMPLE_SERIAL 1: the 3-D sampler queues every kernel on the context's stream (no side streams) */
+enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_SAMPLE_SERIAL = 3, BN_TUNE_COUNT = 8 };
 BN_API int bn_debug_tune(bn_ctx *ctx, int knob, int value);
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
  * generator against the published known-answer vectors. */
