@@ -94,6 +94,7 @@ SIGNATURES = {
     "bn_csc_result_free": (None, [_VP]),
     "bn_post_stream": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _U64, _I64, TILE_SINK, _VP]),
     "bn_debug_last_fit": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "bn_debug_dense_table": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_double, _VP, C.c_int64, _VP]),
     "bn_debug_tune": (C.c_int, [_VP, C.c_int, C.c_int]),
     "bn_debug_write_peak": (C.c_int, [_VP, _I64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }

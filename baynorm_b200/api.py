@@ -456,7 +456,7 @@ def SyntheticControl(Data, BETA_vec, seed=None, ctx=None):
 # --------------------------------------------------------------------------------------
 # R-level functions
 # --------------------------------------------------------------------------------------
-TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS = 0, 1, 2
+TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS, TUNE_SAMPLE_SERIAL = 0, 1, 2, 3
 
 
 def _fit_opts(GR=False, method="spg", maxfeval=500, park_after=0):

@@ -533,6 +533,604 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 8 : 4)
 }
 
 // ---------------------------------------------------------------------------------
+// Version 2 of the 1-D fit: the cost of one evaluation is proportional to the gene's NON-ZEROS, not to the cells.
+//
+//   l(phi) = -phi F(mu/phi)  -  sum_nz x_j log(1 + r beta_j)  +  sum_{1 <= k < kmax} tail_k log1p(k/phi)  +  [x > HMAX]  +  Kc,
+//   F(r) = sum_{all cells j} log(1 + r beta_j),   r = mu/phi
+//
+// (the expression of nb_loglik with log(phi + mu beta_j) = log phi + log(1 + r beta_j); the X log phi terms of the non-zero
+// sum and of the tail sum cancel analytically instead of numerically).
+//  * F depends on the gene only through the scalar r, so it is tabulated ONCE per call: piecewise Chebyshev interpolants of
+//    degree 12 in t = log r on intervals of width 1/4 (F(e^t) is analytic in the strip |Im t| < pi: the interpolation error is
+//    ~50^-13 relative, far below one rounding), node values by compensated summation over the C cells.  An evaluation costs
+//    ~50 FP64 instructions in one thread instead of 3 per cell in every thread.
+//  * The non-zeros of a gene are staged once per call as beta_j, sorted by count (descending).  prod_j u_j^x_j is then a
+//    product of prefix products of the staged order (see nb_loglik2): 2 FP64 instructions per non-zero and trial size
+//    whatever the count, against 14 for x log(phi + mu beta_j) through bn_log, and 8 bytes of coalesced traffic per non-zero
+//    and pass against a packed word plus a gathered BETA sector (40 bytes).  Every multiplication perturbs the logarithm of
+//    the product by <= 2^-53 absolute -- less than the rounding of the partial sums it replaces.
+//  * spg's value at p and its forward-difference partner at p + eps share one pass over the entries (see k_fit2).
+// Results are a pure function of the gene's data (fixed thread map and order); which genes share a launch does not matter.
+// ---------------------------------------------------------------------------------
+#define DT_T0 (-48.0) // table covers r in [e^-48, e^48]; the call builds only the intervals its box and means can reach
+#define DT_NI 384     // intervals of width DT_H = 1/4 in log r
+#define DT_N 13       // Chebyshev nodes / coefficients per interval
+#define DT_STRIDE 16  // doubles per interval: DT_N coefficients (c0 halved), 1 / r_centre, padding
+#define FIT2_HMAX 256 // tail table length (counts beyond: Stirling)
+#define FIT2_CMAX 32  // counts up to here go through the prefix products, larger ones take one logarithm per entry
+
+struct DenseMeta {
+    int i_lo, i_hi;    // intervals built
+    double r_lo, r_hi; // r inside [r_lo, r_hi] is covered
+};
+
+// range of r = mu/phi the solvers can ask for: phi in [lower, upper + eps], mu over the genes with mu > 0
+__global__ void __launch_bounds__(1024) k_dt_range(int64_t G, const double *__restrict__ mu, const double *__restrict__ params,
+                                                   double r_lo_user, double r_hi_user, DenseMeta *__restrict__ meta)
+{
+    __shared__ double smin[32], smax[32];
+    double mn = INFINITY, mx = 0.0;
+    for (int64_t g = threadIdx.x; g < G; g += blockDim.x) {
+        const double v = mu ? mu[g] : 0.0;
+        if (v > 0.0 && v < INFINITY) {
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+    }
+    mn = bn_warp_min(mn);
+    mx = bn_warp_max(mx);
+    if ((threadIdx.x & 31) == 0) {
+        smin[threadIdx.x >> 5] = mn;
+        smax[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; k++) {
+            mn = fmin(mn, smin[k]);
+            mx = fmax(mx, smax[k]);
+        }
+        DenseMeta m;
+        m.i_lo = 1;
+        m.i_hi = 0;
+        m.r_lo = INFINITY;
+        m.r_hi = 0.0;
+        double rl, rh;
+        if (params) { // the fit: box from device memory
+            const double lower = params[0], upper = params[1];
+            rl = mn / (upper * (1.0 + 1e-6) + 1e-6);
+            rh = mx / lower;
+        } else {
+            rl = r_lo_user;
+            rh = r_hi_user;
+        }
+        if (rh > 0.0 && rl <= rh && rl > 0.0 && rh < INFINITY) {
+            int a = (int)floor((log(rl) - DT_T0) * 4.0) - 1, b = (int)floor((log(rh) - DT_T0) * 4.0) + 1;
+            a = a < 0 ? 0 : a;
+            b = b > DT_NI - 1 ? DT_NI - 1 : b;
+            if (a <= b) {
+                m.i_lo = a;
+                m.i_hi = b;
+                // strictly inside the built intervals: the index computed from a rounded log r may be one off at a boundary
+                m.r_lo = exp(DT_T0 + 0.25 * a + 1e-3);
+                m.r_hi = exp(DT_T0 + 0.25 * (b + 1) - 1e-3);
+            }
+        }
+        *meta = m;
+    }
+}
+
+// node values: part[(i * nsplit + s) * DT_N + k] = sum over the cells of split s of log1p(r_k beta_j), compensated
+__global__ void __launch_bounds__(256) k_dt_nodes(int64_t C, const double *__restrict__ beta, const DenseMeta *__restrict__ meta,
+                                                  int nsplit, double *__restrict__ part)
+{
+    const int i = blockIdx.x, s = blockIdx.y;
+    if (i < meta->i_lo || i > meta->i_hi) return;
+    __shared__ double sh[8][DT_N];
+    const double rc = exp(DT_T0 + 0.25 * (i + 0.5));
+    double rk[DT_N], acc[DT_N], cmp[DT_N];
+#pragma unroll
+    for (int k = 0; k < DT_N; k++) {
+        rk[k] = rc * exp(0.125 * cospi((k + 0.5) / DT_N));
+        acc[k] = 0.0;
+        cmp[k] = 0.0;
+    }
+    const int64_t j0 = C * s / nsplit, j1 = C * (s + 1) / nsplit;
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += 256) {
+        const double b = __ldg(beta + j);
+#pragma unroll
+        for (int k = 0; k < DT_N; k++) { // Kahan: the node values carry the accuracy of the whole table
+            const double y = log1p(rk[k] * b) - cmp[k];
+            const double t = acc[k] + y;
+            cmp[k] = (t - acc[k]) - y;
+            acc[k] = t;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < DT_N; k++) {
+        const double v = bn_warp_sum(acc[k] - cmp[k]);
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < DT_N) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
+        part[((int64_t)i * nsplit + s) * DT_N + threadIdx.x] = v;
+    }
+}
+
+// Chebyshev coefficients of every built interval: c_m = (2/N) sum_k f_k cos(m pi (k + 1/2) / N)
+__global__ void __launch_bounds__(32) k_dt_coef(const DenseMeta *__restrict__ meta, int nsplit, const double *__restrict__ part,
+                                                double *__restrict__ coef)
+{
+    const int i = blockIdx.x, lane = threadIdx.x;
+    if (i < meta->i_lo || i > meta->i_hi) return;
+    double f = 0.0, c = 0.0;
+    if (lane < DT_N)
+        for (int s = 0; s < nsplit; s++) {
+            const double y = part[((int64_t)i * nsplit + s) * DT_N + lane] - c;
+            const double t = f + y;
+            c = (t - f) - y;
+            f = t;
+        }
+    double cm = 0.0;
+    for (int k = 0; k < DT_N; k++) {
+        const double fk = __shfl_sync(0xffffffffu, f, k);
+        cm += fk * cospi((double)lane * (k + 0.5) / DT_N);
+    }
+    cm *= 2.0 / DT_N;
+    if (lane == 0) cm *= 0.5;
+    if (lane < DT_N) coef[i * DT_STRIDE + lane] = cm;
+    if (lane == DT_N) coef[i * DT_STRIDE + DT_N] = 1.0 / exp(DT_T0 + 0.25 * (i + 0.5));
+}
+
+// F(r) from the table (r inside [meta.r_lo, meta.r_hi])
+__device__ __forceinline__ double dt_eval(double r, const double *__restrict__ coef, const DenseMeta *__restrict__ meta,
+                                          const BnLogEntry *__restrict__ tab)
+{
+    int i = (int)floor((bn_log(r, tab) - DT_T0) * 4.0);
+    i = i < meta->i_lo ? meta->i_lo : (i > meta->i_hi ? meta->i_hi : i);
+    const double *__restrict__ c = coef + i * DT_STRIDE;
+    // local coordinate from the ratio to the interval centre: log of a number in [0.88, 1.14] keeps full relative accuracy
+    const double x = 8.0 * bn_log(r * __ldg(c + DT_N), tab), x2 = 2.0 * x;
+    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int k = DT_N - 1; k >= 1; k--) {
+        const double b0 = fma(x2, b1, __ldg(c + k) - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return fma(x, b1, __ldg(c) - b2);
+}
+
+// per-gene record written by the staging kernel
+struct GeneMeta2 {
+    double Kbase; // sum x log beta_j - sum lgamma(x + 1)
+    double X;     // sum x
+    int kmax;     // min(FIT2_HMAX, largest count)
+    int n_big;    // stored entries with x > FIT2_HMAX
+};
+
+#define FIT2_NK (FIT2_HMAX + 2) // sort keys: 0 (explicitly stored zero: dropped), 1..HMAX, HMAX + 1 (larger counts)
+
+// Staging, CTA per gene (atomic queue): a counting sort of the gene's stored entries by count, DESCENDING -- entries with
+// x > HMAX first (positions [0, tail[HMAX])), then count c at [tail[c], tail[c - 1]), tail[c] = #{x > c} -- plus the tail
+// table, Kbase and X.  gs[rowptr[g] + position] = beta_j (for x > HMAX: the position of the entry in gm, as raw bits).
+// Every warp owns a contiguous eighth of the gene and keeps the order of its entries, so the staged order is one fixed
+// function of the gene's data (cells ascending inside a count group).
+__global__ void __launch_bounds__(256) k_fit2_stage(int64_t G, const int64_t *__restrict__ rowptr, const uint64_t *__restrict__ gm,
+                                                    const double *__restrict__ beta, const double *__restrict__ logbeta,
+                                                    unsigned long long *__restrict__ queue, double *__restrict__ gs,
+                                                    uint8_t *__restrict__ gx, GeneMeta2 *__restrict__ gmeta,
+                                                    uint32_t *__restrict__ tail_all)
+{
+    __shared__ uint32_t hist[FIT2_HMAX + 1]; // hist[q]: #{x == q + 1} (q = HMAX: larger), then tail[q] = #{x > q}
+    __shared__ uint32_t wh[8][FIT2_NK];      // per-warp counts per key, then the warp's next free position per key
+    __shared__ double red8[8], red8b[8];
+    __shared__ int xmax_sh;
+    __shared__ unsigned long long next_gene;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) next_gene = atomicAdd(queue, 1ULL);
+        for (int q = tid; q < 8 * FIT2_NK; q += 256) (&wh[0][0])[q] = 0;
+        if (tid == 0) xmax_sh = 0;
+        __syncthreads();
+        if (next_gene >= (unsigned long long)G) break;
+        const int64_t gi = (int64_t)next_gene, a = rowptr[gi], nnz = rowptr[gi + 1] - a;
+        const uint64_t *__restrict__ nz = gm + a;
+        const int64_t c0 = nnz * warp / 8, c1 = nnz * (warp + 1) / 8;
+        double kk = 0.0, xs = 0.0;
+        int xm = 0;
+        for (int64_t base = c0; base < c1; base += 32) {
+            const int64_t k = base + lane;
+            int key = -1;
+            if (k < c1) {
+                const uint64_t e0 = __ldg(nz + k);
+                const uint32_t xi = (uint32_t)e0;
+                const double x = (double)xi;
+                kk += x * __ldg(logbeta + (e0 >> 32)) - bn_lfact(x);
+                xs += x;
+                key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
+                xm = max(xm, key);
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, key);
+            if (key > 0 && (same & lt) == 0) wh[warp][key] += (uint32_t)__popc(same);
+            __syncwarp();
+        }
+        atomicMax(&xmax_sh, xm);
+        const double Kbase = bn_group_sum<256>(kk, red8);
+        const double X = bn_group_sum<256>(xs, red8b);
+        __syncthreads();
+        for (int key = 1 + tid; key < FIT2_NK; key += 256) {
+            uint32_t t = 0;
+            for (int w = 0; w < 8; w++) t += wh[w][key];
+            hist[key - 1] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t r = hist[FIT2_HMAX];
+            GeneMeta2 gmv;
+            gmv.Kbase = Kbase;
+            gmv.X = X;
+            gmv.n_big = (int)r;
+            gmv.kmax = min(FIT2_HMAX, xmax_sh);
+            gmeta[gi] = gmv;
+            for (int q = FIT2_HMAX - 1; q >= 0; q--) { // suffix sum: tail[k] = #{x > k}
+                r += hist[q];
+                hist[q] = r;
+            }
+        }
+        __syncthreads();
+        uint32_t *__restrict__ tl = tail_all + gi * (int64_t)(FIT2_HMAX + 1);
+        for (int q = tid; q <= FIT2_HMAX; q += 256) tl[q] = hist[q];
+        for (int key = 1 + tid; key < FIT2_NK; key += 256) {
+            uint32_t pos = key > FIT2_HMAX ? 0u : hist[key]; // first position of the key's group
+            for (int w = 0; w < 8; w++) {
+                const uint32_t n = wh[w][key];
+                wh[w][key] = pos;
+                pos += n;
+            }
+        }
+        __syncthreads();
+        double *__restrict__ out = gs + a;
+        for (int64_t base = c0; base < c1; base += 32) {
+            const int64_t k = base + lane;
+            int key = -1;
+            uint64_t e0 = 0;
+            if (k < c1) {
+                e0 = __ldg(nz + k);
+                const uint32_t xi = (uint32_t)e0;
+                key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, key);
+            const uint32_t pos = key > 0 ? wh[warp][key] : 0u;
+            __syncwarp();
+            if (key > 0) {
+                if ((same & lt) == 0) wh[warp][key] = pos + (uint32_t)__popc(same);
+                const uint32_t at = pos + (uint32_t)__popc(same & lt);
+                out[at] = key <= FIT2_HMAX ? __ldg(beta + (e0 >> 32)) : __longlong_as_double((long long)(a + k));
+                gx[a + at] = (uint8_t)(key <= FIT2_HMAX ? key - 1 : 0); // count - 1 (1..256 in a byte)
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct FitGene2 {
+    const double *gs;     // staged entries of the gene
+    const uint8_t *gx;    // their counts - 1 (entries up to FIT2_HMAX)
+    const uint32_t *tail; // shared memory: tail[k] = #{x > k}, k <= FIT2_HMAX
+    double mu, Kc;
+    int kmax, n_big;
+};
+
+// rare paths of nb_loglik2 as real calls: the evaluation body stays small enough for the instruction cache
+__device__ __noinline__ double bn_log_far(double x, const BnLogEntry *__restrict__ tab) { return bn_log(x, tab); }
+
+// entries [tid, nb) step TPG of the gene's staged order (counts beyond the tail table): -x log u plus Stirling's series for
+// lgamma(x + phi) - lgamma(HMAX + phi) - (x - HMAX) log phi
+__device__ __noinline__ double fit2_big(const double *__restrict__ gs, int nb, int tid, int tpg, const uint64_t *__restrict__ gm,
+                                        const double *__restrict__ beta, double r, double phi, const BnLogEntry *__restrict__ tab)
+{
+    const double lgref = bn_lgamma_stirling(phi + (double)FIT2_HMAX, tab), lphi = bn_log(phi, tab);
+    double s = 0.0;
+    for (int k = tid; k < nb; k += tpg) {
+        const uint64_t e0 = __ldg(gm + __double_as_longlong(__ldg(gs + k)));
+        const double x = (double)(uint32_t)e0, b = __ldg(beta + (e0 >> 32));
+        s = fma(-x, bn_log(fma(r, b, 1.0), tab), s);
+        s += (bn_lgamma_stirling(x + phi, tab) - lgref) - (x - (double)FIT2_HMAX) * lphi;
+    }
+    return s;
+}
+
+// the dense part summed directly (an r the table was not built for: cannot happen for the box the table was built from)
+__device__ __noinline__ double fit2_dense_direct(const double *__restrict__ beta, int64_t C, int tid, int tpg, double r,
+                                                 const BnLogEntry *__restrict__ tab)
+{
+    double d = 0.0;
+    for (int64_t j = tid; j < C; j += tpg) d += bn_log1p_pos(r * __ldg(beta + j), tab);
+    return d;
+}
+
+// -l at NP trial sizes in ONE pass over the gene's staged entries.
+//
+// sum_nz x_j log u_j (u_j = 1 + r beta_j) without a logarithm per entry: with the entries sorted by count, descending,
+//   prod_j u_j^x_j = prod_{c >= 1} S_c,   S_c = prod_{x_j >= c} u_j  (a prefix of the staged order),
+// so a thread walks its entries once, multiplies each u into the running prefix product S (fma + mul per entry and trial
+// size, whatever the count) and multiplies S into T each time it passes from count c to c - 1.  Exponent budgets keep S and T
+// inside the double range: before either could overflow -- and across runs of absent counts, where crossings would
+// otherwise cost a multiplication each -- S is folded as acc += c log S (its entries still have c crossings ahead), T as
+// acc += log T.  Every multiplication perturbs the logarithm of its product by <= 2^-53 absolute.  Counts above FIT2_CMAX
+// (few entries per count and thread: the crossings would cost more than they save) take one logarithm per entry.
+template <int TPG, int NP>
+__device__ __forceinline__ void nb_loglik2(const FitGene2 &g, const double *phi, double *val, const uint64_t *__restrict__ gm,
+                                           const double *__restrict__ beta, int64_t C, double beta_max, const double *__restrict__ coef,
+                                           const DenseMeta *__restrict__ meta, const BnLogEntry *__restrict__ tab, double *scratch, int tid)
+{
+    double r[NP], S[NP], T[NP], acc[NP];
+    double rmax = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        r[p] = g.mu / phi[p];
+        rmax = fmax(rmax, r[p]);
+        S[p] = 1.0;
+        T[p] = 1.0;
+        acc[p] = 0.0;
+    }
+    int ub = ((__double2hiint(fma(rmax, beta_max, 1.0)) >> 20) & 0x7ff) - 1022; // u < 2^ub for every cell and trial size
+    ub = ub > 1000 ? 1000 : ub;
+    const uint32_t *__restrict__ tail = g.tail;
+    const int n = (int)tail[0]; // staged entries (a gene has fewer than 2^31: one per cell at most)
+    int eS = 0, eT = 0, level = g.kmax < FIT2_CMAX ? g.kmax : FIT2_CMAX;
+    int nextb = level >= 1 ? (int)tail[level - 1] : n; // first position whose count is below `level`
+#define FIT2_FOLD_S()                                                                  \
+    {                                                                                  \
+        _Pragma("unroll") for (int p = 0; p < NP; p++)                                 \
+        {                                                                              \
+            acc[p] = fma((double)level, bn_log_far(S[p], tab), acc[p]);                \
+            S[p] = 1.0;                                                                \
+        }                                                                              \
+        eS = 0;                                                                        \
+    }
+#define FIT2_ENTRY(kk_, b_)                                                            \
+    if ((kk_) < n) {                                                                   \
+        while ((kk_) >= nextb) {                                                       \
+            if (eS) {                                                                  \
+                const bool gap = level >= 2 && (int)tail[level - 2] == nextb;          \
+                if (gap || eT + eS > 1000) {                                           \
+                    FIT2_FOLD_S()                                                      \
+                    if (eT > 500) {                                                    \
+                        _Pragma("unroll") for (int p = 0; p < NP; p++)                 \
+                        {                                                              \
+                            acc[p] += bn_log_far(T[p], tab);                           \
+                            T[p] = 1.0;                                                \
+                        }                                                              \
+                        eT = 0;                                                        \
+                    }                                                                  \
+                } else {                                                               \
+                    _Pragma("unroll") for (int p = 0; p < NP; p++) T[p] *= S[p];       \
+                    eT += eS;                                                          \
+                }                                                                      \
+            }                                                                          \
+            level--;                                                                   \
+            nextb = level >= 1 ? (int)tail[level - 1] : n;                             \
+        }                                                                              \
+        if (eS + ub > 1000) FIT2_FOLD_S()                                              \
+        _Pragma("unroll") for (int p = 0; p < NP; p++) S[p] *= fma(r[p], (b_), 1.0);   \
+        eS += ub;                                                                      \
+    }
+    const double *__restrict__ gs = g.gs;
+    const int nm = g.kmax > FIT2_CMAX ? (int)tail[FIT2_CMAX] : g.n_big; // start of the prefix-product section
+    for (int k = nm + tid; k < n; k += 4 * TPG) {
+        const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG;
+        const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
+                     b3 = k3 < n ? __ldg(gs + k3) : 0.0;
+        FIT2_ENTRY(k, b0)
+        FIT2_ENTRY(k1, b1)
+        FIT2_ENTRY(k2, b2)
+        FIT2_ENTRY(k3, b3)
+    }
+#undef FIT2_ENTRY
+#undef FIT2_FOLD_S
+    double s[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (eS) acc[p] = fma((double)level, bn_log_far(S[p], tab), acc[p]);
+        if (eT) acc[p] += bn_log_far(T[p], tab);
+        s[p] = -acc[p];
+    }
+    if (g.kmax > FIT2_CMAX) {
+        const uint8_t *__restrict__ gx = g.gx;
+        int k = g.n_big + tid;
+        for (; k + TPG < nm; k += 2 * TPG) {
+            const double b0 = __ldg(gs + k), b1 = __ldg(gs + k + TPG);
+            const double x0 = (double)((int)__ldg(gx + k) + 1), x1 = (double)((int)__ldg(gx + k + TPG) + 1);
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                s[p] = fma(-x0, bn_log(fma(r[p], b0, 1.0), tab), s[p]);
+                s[p] = fma(-x1, bn_log(fma(r[p], b1, 1.0), tab), s[p]);
+            }
+        }
+        if (k < nm) {
+            const double b0 = __ldg(gs + k), x0 = (double)((int)__ldg(gx + k) + 1);
+#pragma unroll
+            for (int p = 0; p < NP; p++) s[p] = fma(-x0, bn_log(fma(r[p], b0, 1.0), tab), s[p]);
+        }
+        if (g.n_big) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) s[p] += fit2_big(gs, g.n_big, tid, TPG, gm, beta, r[p], phi[p], tab);
+        }
+    }
+    if (g.kmax > 1) {
+        double iphi[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) iphi[p] = 1.0 / phi[p];
+        for (int q = 1 + tid; q < g.kmax; q += TPG) {
+            const double t = (double)tail[q], qd = (double)q;
+#pragma unroll
+            for (int p = 0; p < NP; p++) s[p] = fma(t, bn_log1p_pos(qd * iphi[p], tab), s[p]);
+        }
+    }
+    // the dense part: every cell, through the table (thread p serves trial size p)
+    {
+        const bool mine = tid < NP;
+        double rr = r[0], ph = phi[0];
+#pragma unroll
+        for (int p = 1; p < NP; p++)
+            if (tid == p) {
+                rr = r[p];
+                ph = phi[p];
+            }
+        bool covered = true;
+#pragma unroll
+        for (int p = 0; p < NP; p++) covered = covered && r[p] >= meta->r_lo && r[p] <= meta->r_hi;
+        if (covered) {
+            if (mine) {
+                const double d = -ph * dt_eval(rr, coef, meta, tab);
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (tid == p) s[p] += d;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; p++) s[p] = fma(-phi[p], fit2_dense_direct(beta, C, tid, TPG, r[p], tab), s[p]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) s[p] = bn_warp_sum(s[p]);
+    if (TPG != 32) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        __syncthreads(); // scratch may still be read by the previous call
+        if (l == 0) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) scratch[p * (TPG / 32) + w] = s[p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < TPG / 32; k++) t += scratch[p * (TPG / 32) + k];
+            s[p] = t;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) val[p] = -(s[p] + g.Kc);
+}
+
+// gene lists of the two geometries: warp per gene below FIT2_SPLIT stored entries, CTA per gene from there on
+#define FIT2_SPLIT 4096
+__global__ void __launch_bounds__(256) k_fit2_lists(int64_t G, const int64_t *__restrict__ rowptr, int split, int32_t *__restrict__ small,
+                                                    int32_t *__restrict__ big, unsigned int *__restrict__ counts)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const bool isbig = rowptr[g + 1] - rowptr[g] >= split;
+    const unsigned slot = atomicAdd(counts + (isbig ? 1 : 0), 1u);
+    (isbig ? big : small)[slot] = (int32_t)g;
+}
+
+// spg asks for -l(p) and then, unless the line search rejects p, for -l(p + eps) (its forward-difference gradient): both are
+// evaluated in the same pass over the gene (the entries are read once, the second value costs two more FP64 instructions per
+// entry) and the second is handed over only if it is what the solver asks for next -- the sequence of values the solver sees,
+// and the count of evaluations it consumed, are those of one-at-a-time evaluation.
+template <int TPG, int METHOD>
+__global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
+    k_fit2(const int32_t *__restrict__ list, const unsigned int *__restrict__ count, int64_t C, const int64_t *__restrict__ rowptr,
+           const uint64_t *__restrict__ gm, const double *__restrict__ gs, const uint8_t *__restrict__ gx,
+           const GeneMeta2 *__restrict__ gmeta, const uint32_t *__restrict__ tail_all, const double *__restrict__ beta,
+           const double *__restrict__ mu0,
+           const double *__restrict__ size0, const double *__restrict__ params, const double *__restrict__ coef,
+           const DenseMeta *__restrict__ meta, FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
+           int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
+{
+    constexpr int GPC = TPG == 32 ? 4 : 1; // genes in flight per CTA
+    const double lower = params[0], upper = params[1], beta_max = params[2];
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    __shared__ double scratch[16];
+    __shared__ uint32_t tail_sh[GPC][FIT2_HMAX + 1];
+    __shared__ unsigned long long next_gene;
+    bn_log_table_load(tab);
+    __syncthreads();
+    const int tid = (TPG == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    uint32_t *tl = tail_sh[TPG == 32 ? (threadIdx.x >> 5) : 0];
+    const unsigned long long n = *count;
+    for (;;) {
+        unsigned long long gq;
+        if (TPG == 32) {
+            if (tid == 0) gq = atomicAdd(queue, 1ULL);
+            gq = __shfl_sync(0xffffffffu, gq, 0);
+        } else {
+            __syncthreads();
+            if (tid == 0) next_gene = atomicAdd(queue, 1ULL);
+            __syncthreads();
+            gq = next_gene;
+        }
+        if (gq >= n) break;
+        const int64_t gi = (int64_t)list[gq];
+        const int64_t a = rowptr[gi];
+        const GeneMeta2 gmv = gmeta[gi];
+        for (int q = tid; q <= FIT2_HMAX; q += TPG) tl[q] = __ldg(tail_all + gi * (int64_t)(FIT2_HMAX + 1) + q);
+        if (TPG == 32) __syncwarp();
+        else __syncthreads();
+        FitGene2 g;
+        g.gs = gs + a;
+        g.gx = gx + a;
+        g.tail = tl;
+        g.mu = mu0[gi];
+        g.kmax = gmv.kmax;
+        g.n_big = gmv.n_big;
+        const double par = size0[gi];
+        double res = par;
+        int conv = 0, nfe = 0;
+        if (!(g.mu > 0.0)) {
+            // flat likelihood (mean 0): spg's first projected gradient is 0, it returns the projected start
+            res = proj(par, lower, upper);
+            if (METHOD == BN_FIT_SPG) nfe = 2;
+        } else {
+            g.Kc = fma(gmv.X, log(g.mu), gmv.Kbase);
+            if (METHOD == BN_FIT_BRENT) {
+                BrentState st;
+                st.init(lower, upper);
+                bool more = true;
+                while (more) {
+                    double at[1] = {st.next}, v[1];
+                    nb_loglik2<TPG, 1>(g, at, v, gm, beta, C, beta_max, coef, meta, tab, scratch, tid);
+                    nfe++;
+                    more = st.step(v[0], o);
+                }
+                res = st.next;
+                conv = st.conv;
+            } else {
+                SpgState st;
+                st.init(par, lower, upper, o);
+                bool more = true;
+                while (more) {
+                    double at[2] = {st.next, st.next + o.eps}, v[2];
+                    nb_loglik2<TPG, 2>(g, at, v, gm, beta, C, beta_max, coef, meta, tab, scratch, tid);
+                    nfe++;
+                    more = st.step(v[0], o);
+                    if (more && !st.next_is_grad && st.next == at[1] && (st.phase == SpgState::INIT_G || st.phase == SpgState::GRAD)) {
+                        nfe++;
+                        more = st.step(v[1], o);
+                    }
+                }
+                res = st.next;
+                conv = st.conv;
+            }
+        }
+        if (tid == 0) {
+            size_out[gi] = res;
+            if (conv_out) conv_out[gi] = conv;
+            if (nfe_out) nfe_out[gi] = nfe;
+        }
+        if (TPG == 32) __syncwarp(); // the next gene overwrites this warp's tail table
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Multi-slot variant for long genes (C >= 8192): one 256-thread CTA evaluates FIT_NS genes
 // ("slots") per sweep over the cells, each at its own trial size.  Every beta_j fetched from
 // L1/L2 feeds FIT_NS likelihoods, which is what bounds the single-slot kernel at 1e5+ cells (each
@@ -1305,7 +1903,56 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     ctx->last_fit[2] = o.evcap;
     ctx->last_fit[3] = grad ? 1 : 0;
 #define FIT_ARGS m->G, m->C, m->rowptr, m->gm, d_beta, lb.p, d_mu0, d_size0, params.p, o, q.p, d_size_out, d_conv, d_nfe
-    if (m->C >= 8192) {
+    const bool sparse_mat = (double)m->nnz <= 0.2 * (double)m->G * (double)m->C;
+    if (!grad && (ctx->tune[BN_TUNE_FIT_VARIANT] == 5 || (ctx->tune[BN_TUNE_FIT_VARIANT] == 0 && sparse_mat))) {
+        // version 2 (see k_fit2): dense part from the per-call table, non-zeros staged by count.  Measured against the
+        // first-generation kernels: 33k x 100k at 8 % non-zeros 37 -> 14.5 ms, 33k x 1.3M 598 -> 205 ms; on matrices with
+        // >= 20 % non-zeros and counts in the hundreds (config 2) most entries take the one-logarithm path and the
+        // first-generation sweep kernel is faster (7.5 against 9.8 ms): those keep it.
+        ctx->last_fit[0] = 5;
+        const int64_t G = m->G, nnz = m->nnz;
+        struct { double *p; } gs, dt;
+        struct { uint8_t *p; } gx;
+        struct { uint32_t *p; } tails;
+        struct { GeneMeta2 *p; } gmeta;
+        struct { int32_t *p; } lists;
+        constexpr int NSPLIT = 6;
+        const size_t dt_doubles = (size_t)DT_NI * DT_STRIDE + (size_t)DT_NI * NSPLIT * DT_N + 8;
+        BN_TRY(bn_ctx_scratch(ctx, 14, (size_t)std::max<int64_t>(nnz, 1) * 8, (void **)&gs.p));
+        BN_TRY(bn_ctx_scratch(ctx, 19, (size_t)std::max<int64_t>(nnz, 1), (void **)&gx.p));
+        BN_TRY(bn_ctx_scratch(ctx, 15, (size_t)G * (FIT2_HMAX + 1) * 4, (void **)&tails.p));
+        BN_TRY(bn_ctx_scratch(ctx, 16, (size_t)G * sizeof(GeneMeta2), (void **)&gmeta.p));
+        BN_TRY(bn_ctx_scratch(ctx, 17, (size_t)G * 2 * 4 + 64, (void **)&lists.p));
+        BN_TRY(bn_ctx_scratch(ctx, 18, dt_doubles * 8, (void **)&dt.p));
+        double *coef = dt.p, *part = dt.p + (size_t)DT_NI * DT_STRIDE;
+        DenseMeta *meta = reinterpret_cast<DenseMeta *>(part + (size_t)DT_NI * NSPLIT * DT_N);
+        DevBuf<unsigned long long> q2; // queues: staging, warp-per-gene fit, CTA-per-gene fit
+        DevBuf<unsigned int> cnt2;
+        BN_TRY(q2.alloc(ctx, 4));
+        BN_TRY(cnt2.alloc(ctx, 2));
+        BN_CUDA(ctx, cudaMemsetAsync(q2.p, 0, 32, ctx->stream));
+        BN_CUDA(ctx, cudaMemsetAsync(cnt2.p, 0, 8, ctx->stream));
+        BN_LAUNCH(ctx, k_dt_range, 1, 1024, 0, G, d_mu0, params.p, 0.0, 0.0, meta);
+        BN_LAUNCH(ctx, k_dt_nodes, dim3(DT_NI, NSPLIT), 256, 0, m->C, d_beta, meta, NSPLIT, part);
+        BN_LAUNCH(ctx, k_dt_coef, DT_NI, 32, 0, meta, NSPLIT, part, coef);
+        BN_LAUNCH(ctx, k_fit2_stage, (int)std::min<int64_t>(G, (int64_t)sms * 8), 256, 0, G, m->rowptr, m->gm, d_beta, lb.p, q2.p, gs.p, gx.p, gmeta.p,
+                  tails.p);
+        int32_t *l_small = lists.p, *l_big = lists.p + G;
+        const int split = ctx->tune[BN_TUNE_FIT_SPLIT] > 0 ? ctx->tune[BN_TUNE_FIT_SPLIT] : FIT2_SPLIT;
+        BN_LAUNCH(ctx, k_fit2_lists, (unsigned)((G + 255) / 256), 256, 0, G, m->rowptr, split, l_small, l_big, cnt2.p);
+#define FIT2_ARGS(L, K, Q) L, cnt2.p + K, m->C, m->rowptr, m->gm, gs.p, gx.p, gmeta.p, tails.p, d_beta, d_mu0, d_size0, params.p, coef, meta, o, q2.p + Q, \
+    d_size_out, d_conv, d_nfe
+        // the long genes first: their tail is what ends the phase
+        const int grid_big = (int)std::min<int64_t>(G, (int64_t)sms * 3), grid_small = (int)std::min<int64_t>((G + 3) / 4, (int64_t)sms * 6);
+        if (o.method == BN_FIT_BRENT) {
+            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_BRENT>), grid_big, 256, 0, FIT2_ARGS(l_big, 1, 2));
+            BN_LAUNCH(ctx, (k_fit2<32, BN_FIT_BRENT>), grid_small, 128, 0, FIT2_ARGS(l_small, 0, 1));
+        } else {
+            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_SPG>), grid_big, 256, 0, FIT2_ARGS(l_big, 1, 2));
+            BN_LAUNCH(ctx, (k_fit2<32, BN_FIT_SPG>), grid_small, 128, 0, FIT2_ARGS(l_small, 0, 1));
+        }
+#undef FIT2_ARGS
+    } else if (m->C >= 8192) {
         // long genes: a whole CTA per gene keeps every gene's evaluations short and the tail small
         const int grid = (int)std::min<int64_t>(m->G, (int64_t)sms * 12);
         const int force = ctx->tune[BN_TUNE_FIT_VARIANT]; // A/B switch of profiling runs (bn_debug_tune)
@@ -1323,7 +1970,7 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
             // than 3 x 78 registers, 2 x 112 is 25 % slower).  Dense matrices (>= 20 % non-zero), where the per-gene
             // non-zero loop dominates and BETA re-use across genes matters less: 2 genes per sweep at 6 CTAs per SM
             // (40 registers) is 3.5 % faster; 3 x 5 and 6 x 3 are slower on both.
-            const bool dense = force ? force == 2 : (double)m->nnz > 0.2 * (double)m->G * (double)m->C;
+            const bool dense = force == 2 || ((force == 0 || force == 4) && (double)m->nnz > 0.2 * (double)m->G * (double)m->C);
             ctx->last_fit[0] = dense ? 2 : 3;
             if (dense)
                 BN_LAUNCH(ctx, (k_fit_size_ms<6, 4, 2>), (int)std::min<int64_t>((m->G + 1) / 2, (int64_t)sms * 6), 256, 0, FIT_ARGS,
@@ -1537,6 +2184,42 @@ extern "C" int bn_fit_size_mu(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, co
     BN_TRY(mo.commit(ctx));
     BN_TRY(co.commit(ctx));
     BN_TRY(no.commit(ctx));
+    return bn_sync(ctx);
+}
+
+// debug hook: the dense-part table F(r) = sum_j log(1 + r BETA_j) built for [r_lo, r_hi] and evaluated at r[0..n)
+__global__ void __launch_bounds__(256) k_dt_debug(int64_t n, const double *__restrict__ r, const double *__restrict__ coef,
+                                                  const DenseMeta *__restrict__ meta, double *__restrict__ out)
+{
+    __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
+    bn_log_table_load(tab);
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += gridDim.x * (int64_t)blockDim.x) {
+        const double v = r[k];
+        out[k] = (v >= meta->r_lo && v <= meta->r_hi) ? dt_eval(v, coef, meta, tab) : nan("");
+    }
+}
+
+extern "C" int bn_debug_dense_table(bn_ctx *ctx, const double *BETA, int64_t C, double r_lo, double r_hi, const double *r, int64_t n,
+                                    double *out)
+{
+    if (!ctx || !BETA || !r || !out || C <= 0 || n <= 0) return BN_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DevIn<double> b, dr;
+    BN_TRY(b.bind(ctx, BETA, (size_t)C));
+    BN_TRY(dr.bind(ctx, r, (size_t)n));
+    DevOut<double> o;
+    BN_TRY(o.bind(ctx, out, (size_t)n));
+    constexpr int NSPLIT = 6;
+    DevBuf<double> dt;
+    BN_TRY(dt.alloc(ctx, (size_t)DT_NI * DT_STRIDE + (size_t)DT_NI * NSPLIT * DT_N + 8));
+    double *coef = dt.p, *part = dt.p + (size_t)DT_NI * DT_STRIDE;
+    DenseMeta *meta = reinterpret_cast<DenseMeta *>(part + (size_t)DT_NI * NSPLIT * DT_N);
+    BN_LAUNCH(ctx, k_dt_range, 1, 1024, 0, (int64_t)0, (const double *)nullptr, (const double *)nullptr, r_lo, r_hi, meta);
+    BN_LAUNCH(ctx, k_dt_nodes, dim3(DT_NI, NSPLIT), 256, 0, C, b.p, meta, NSPLIT, part);
+    BN_LAUNCH(ctx, k_dt_coef, DT_NI, 32, 0, meta, NSPLIT, part, coef);
+    BN_LAUNCH(ctx, k_dt_debug, 64, 256, 0, n, dr.p, coef, meta, o.p);
+    BN_TRY(o.commit(ctx));
     return bn_sync(ctx);
 }
 

@@ -28,8 +28,8 @@ struct bn_ctx {
     // grow-only device scratch kept across calls (slots 0-1, 8-9: the 3-D sampler's lists and side buffers; 2-4: counters of the
     // gene-major build; 5: DownSampling's list; 6-7: result tiles): re-allocating GB-sized buffers per call through the stream-ordered
     // pool was measured to stall the host for 5-400 ms every few calls
-    void *scratch[20] = {};        // slots 10-14: the second set of the 3-D sampler's per-chunk buffers
-    size_t scratch_bytes[20] = {};
+    void *scratch[28] = {};        // slots 10-14: the second set of the 3-D sampler's per-chunk buffers
+    size_t scratch_bytes[28] = {};
     // side streams of the 3-D sampler (bn_sample.cu): [0] prepares chunk c + 1 (classification, side-buffer draws) while the
     // main kernel of chunk c runs on `stream`; [1..4] carry the table classes that run next to each other
     cudaStream_t aux[5] = {};

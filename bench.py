@@ -207,6 +207,9 @@ def run_ours(args):
     else:
         g0, G, G_total = rank * Gt, Gt, Gt * world
     ctx = bn.Context(local)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        ctx.tune(int(k), int(v))
     if world > 1:
         bdist.install_torch_allreduce(ctx, rank, world)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -391,7 +394,8 @@ def run_ours(args):
             "config": {"workload": cfg["name"], "genes": int(G_total), "genes_per_gpu": int(G), "cells": C, "nnz": int(nnz_job),
                        "nnz_fraction": rho, "S": S, "groups": groups, "outputs": list(cfg["out"]), "solver": args.solver,
                        "l2": "inputs larger than L2 (CSC %.2f GB per GPU, output tile %.2f GB)" % (nnz * 12 / 1e9, d_out.numel() * 8 / 1e9),
-                       "parallelism": "gene blocks x%d, all-reduce of per-cell totals + 3 small stats per prior set" % world},
+                       "parallelism": "gene blocks x%d, all-reduce of per-cell totals + 3 small stats per prior set" % world,
+                       **({"tune": args.tune} if args.tune else {})},
             "fit": {"genes_per_s": genes_job / fit_s, "ms": fit_s * 1e3,
                     "mean_evaluations_per_gene": evals / genes_rank,
                     "max_evaluations_per_gene": float(nfe.max().item()),
@@ -655,6 +659,8 @@ def main():
     ap.add_argument("--solver", default="spg", choices=["spg", "brent"])
     ap.add_argument("--tile-gb", type=float, default=8.0, help="recycled HBM output tile")
     ap.add_argument("--e2e-out-gb", type=float, default=48.0, help="result bytes delivered to the host per e2e step and rank")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="profiling A/B switch (bn_debug_tune), e.g. 4=16384; recorded in config.tune")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skips cpu_baseline and parity")
     ap.add_argument("--weak", action="store_true", help="config 5: a full 33k-gene block per rank instead of 33k / N")

@@ -279,14 +279,21 @@ BN_API int bn_debug_write_peak(bn_ctx *ctx, int64_t bytes, int planes, int run, 
 /* ---- debug ------------------------------------------------------------------------- */
 /* What the last likelihood fit of this context launched (valid after the call returned):
  * out[0] = kernel variant (0 warp per gene, 1 CTA per gene, 2 sweep kernel 2 genes x 6 CTAs/SM,
- *          3 sweep kernel 4 genes x 4 CTAs/SM, 4 the 2-D fit), out[1] = genes the sweep kernel parked for the
+ *          3 sweep kernel 4 genes x 4 CTAs/SM, 4 the 2-D fit, 5 version 2: k_fit2), out[1] = genes the sweep kernel parked for the
  *          cluster kernel, out[2] = park_after in effect, out[3] = 1 if the analytic gradient was used. */
 BN_API int bn_debug_last_fit(const bn_ctx *ctx, int64_t out[4]);
+/* The likelihood fit's table of the dense part F(r) = sum_j log(1 + r BETA_j) (all C cells), built for r in [r_lo, r_hi] and
+ * evaluated at r[0..n): out[k] = F(r[k]), NaN outside the range (tests pin it against extended-precision sums). */
+BN_API int bn_debug_dense_table(bn_ctx *ctx, const double *BETA, int64_t C, double r_lo, double r_hi, const double *r, int64_t n,
+                                double *out);
 /* A/B switches for profiling runs (the product never reads the environment).  value 0 restores the default.
- *   BN_TUNE_FIT_VARIANT   1..3: force that fit kernel variant for long genes (see bn_debug_last_fit)
+ *   BN_TUNE_FIT_VARIANT   1..3: force that first-generation fit kernel for long genes, 4: the first-generation kernels chosen by
+ *                         shape, 5: version 2 (the table + staged-entries kernels).  Default 0: version 2 for matrices with
+ *                         at most 20 % non-zeros, first generation otherwise (see bn_debug_last_fit)
  *   BN_TUNE_SAMPLE_NCS    columns walked per CTA by the 3-D sampler
- *   BN_TUNE_SAMPLE_SERIAL 1: the 3-D sampler queues every kernel on the context's stream (no side streams) */
-enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_SAMPLE_SERIAL = 3, BN_TUNE_COUNT = 8 };
+ *   BN_TUNE_SAMPLE_SERIAL 1: the 3-D sampler queues every kernel on the context's stream (no side streams)
+ *   BN_TUNE_FIT_SPLIT     version 2 of the fit: genes with at least this many stored entries get a CTA, the others a warp */
+enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_SAMPLE_SERIAL = 3, BN_TUNE_FIT_SPLIT = 4, BN_TUNE_COUNT = 8 };
 BN_API int bn_debug_tune(bn_ctx *ctx, int knob, int value);
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
  * generator against the published known-answer vectors. */

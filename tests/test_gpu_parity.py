@@ -308,36 +308,99 @@ def _assert_fit_matches_oracle(oracle, d, got, conv, tag):
     assert np.array_equal(want == hi, got == hi) and np.array_equal(want == lo, got == lo)
 
 
-def test_fit_multislot_sparse_kernel(bn, ctx, oracle, long_sparse):
-    """k_fit_size_ms<4,4,4>: the kernel BASELINE configs 3, 4 and 5 run (R/PRIOR_FUNCTIONS.R:446-456 per gene)."""
+def test_fit_long_sparse_genes(bn, ctx, oracle, long_sparse):
+    """The shape class of BASELINE configs 3, 4 and 5 (R/PRIOR_FUNCTIONS.R:446-456 per gene): version 2 of the fit (dense part
+    from the per-call table, non-zeros staged by count: k_fit2) by default, and the first-generation kernels -- CTA per gene,
+    2 and 4 genes per sweep (k_fit_size_ms<4,4,4>) -- behind the tuning switch.  All are the same function of the data."""
     d = long_sparse
     assert (d["X"] != 0).mean() < 0.2
     M = bn.Check_input(d["X"], ctx)
     got, conv, nfe = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], SIZE_lower=d["lo"], SIZE_upper=d["hi"], return_info=True)
     info = ctx.last_fit()
-    assert info["variant"] == 3 and info["park_after"] == 128, info
-    _assert_fit_matches_oracle(oracle, d, got, conv, "multi-slot sparse")
+    assert info["variant"] == 5, info
+    _assert_fit_matches_oracle(oracle, d, got, conv, "version 2")
     tot = (d["cnt"][:, 0] + d["cnt"][:, 1]).sum()
     # evaluation counts: same order, not equal -- near the optimum the oracle's forward-difference gradient is dominated
     # by the rounding noise of its sequential 8400-term sum (~1e-3 >> gtol), so it stops on ftol a few steps later than
-    # the GPU, whose tree-ordered sums are less noisy
+    # the GPU, whose sums are less noisy
     print("    evaluations: GPU %d, oracle %d" % (int(nfe.sum()), int(tot)))
     assert 0.7 * tot <= int(nfe.sum()) <= 1.1 * tot, (int(nfe.sum()), int(tot))
-    # the three kernels that can run these genes are the same function of the data: CTA per gene, 2 per sweep, 4 per sweep
-    for variant in (1, 2):
+    res = {}
+    for variant in (1, 2, 3):
         ctx.tune(bn.api.TUNE_FIT_VARIANT, variant)
         try:
             alt, conv_a, _ = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], SIZE_lower=d["lo"], SIZE_upper=d["hi"],
                                        return_info=True)
             assert ctx.last_fit()["variant"] == variant
+            if variant == 3:
+                assert ctx.last_fit()["park_after"] == 128
         finally:
             ctx.tune(bn.api.TUNE_FIT_VARIANT, 0)
+        res[variant] = alt
         assert np.array_equal(conv_a, conv)
-        if variant == 2:
-            assert np.array_equal(alt, got)       # same per-thread cell map and summation order: bit-identical
+        _assert_fit_matches_oracle(oracle, d, alt, conv_a, "first-generation kernel %d" % variant)
+        ra = rel_err(alt, got)
+        assert (ra <= 1e-6).mean() >= d["jitter_frac"] - 0.05 and ra.max() <= 3.0 * d["jitter_max"]
+    assert np.array_equal(res[2], res[3])       # same per-thread cell map and summation order: bit-identical
+
+
+def test_fit_dense_part_table(bn, ctx):
+    """Version 2 of the fit reads the all-cells term F(r) = sum_j log(1 + r BETA_j) of the likelihood
+    (the x = 0 branch of dnbinom_mu summed over the cells, src/bayNorm_main.cpp:928-943) from a per-call Chebyshev table:
+    pinned against 80-bit sums over eleven decades of r, for a short and a long BETA vector."""
+    import ctypes as CT
+    from baynorm_b200.api import _ptr
+    rng = np.random.default_rng(3)
+    for C in (137, 60000):
+        beta = np.clip(rng.lognormal(0.0, 0.4, C) * 0.06, 0.005, 0.5)
+        r = np.exp(rng.uniform(np.log(2e-6), np.log(3e5), 4000))
+        out = np.empty_like(r)
+        ctx.check(ctx.lib.bn_debug_dense_table(ctx.h, _ptr(beta), C, 1e-6, 1e6, _ptr(r), r.size, _ptr(out)))
+        bl = beta.astype(np.longdouble)
+        want = np.array([float(np.log1p(np.longdouble(v) * bl).sum()) for v in r[:400]])
+        err = np.abs(out[:400] - want) / want
+        print("C = %d: table vs 80-bit sum, max rel %.2e, median %.2e" % (C, err.max(), np.median(err)))
+        assert np.isfinite(out).all() and err.max() <= 4e-15
+        # outside the built range: NaN (the kernels then sum the cells directly)
+        r2 = np.array([1e-9, 1e9])
+        o2 = np.empty(2)
+        ctx.check(ctx.lib.bn_debug_dense_table(ctx.h, _ptr(beta), C, 1e-6, 1e6, _ptr(r2), 2, _ptr(o2)))
+        assert np.isnan(o2).all()
+
+
+@pytest.mark.parametrize("which", ["fixture", "dense50"])
+def test_fit_versions_agree(bn, ctx, oracle, dense50, fixture_data, which):
+    """Version 2 against the first-generation kernels on short genes (warp per gene), spg and Brent: the same likelihood
+    evaluated two ways -- Brent's bracketed arg-max must agree to ~1e-7, spg up to its forward-difference jitter."""
+    d = fixture_data if which == "fixture" else dense50
+    X, beta = (d["inputdata"], d["inputbeta"]) if which == "fixture" else (d["X"], d["beta"])
+    Mo = oracle.CSC.from_dense(X)
+    Po = oracle.Prior_fun(Mo, beta, BB_SIZE=False)
+    mu0, s0 = Po["MME_prior"]["MME_MU"], Po["MME_prior"]["MME_SIZE"]
+    lo, hi = float(s0.min()), float(np.ceil(s0.max()))
+    M = bn.Check_input(X, ctx)
+    for method in ("spg", "brent"):
+        kw = dict(SIZE_lower=lo, SIZE_upper=hi, return_info=True, method=method)
+        ctx.tune(bn.api.TUNE_FIT_VARIANT, 5)
+        try:
+            a, conv_a, nfe_a = bn.BB_Fun(M, beta, mu0, s0, **kw)
+            assert ctx.last_fit()["variant"] == 5
+        finally:
+            ctx.tune(bn.api.TUNE_FIT_VARIANT, 0)
+        ctx.tune(bn.api.TUNE_FIT_VARIANT, 4)
+        try:
+            b, conv_b, nfe_b = bn.BB_Fun(M, beta, mu0, s0, **kw)
+            assert ctx.last_fit()["variant"] in (0, 2, 3)
+        finally:
+            ctx.tune(bn.api.TUNE_FIT_VARIANT, 0)
+        re = rel_err(a, b)
+        print("%s %s: version 2 vs first generation: median %.2e max %.2e, <=1e-6 %.1f%%; evaluations %d vs %d"
+              % (which, method, np.median(re), re.max(), 100 * (re <= 1e-6).mean(), nfe_a.sum(), nfe_b.sum()))
+        assert np.array_equal(conv_a, conv_b)
+        if method == "brent":
+            assert re.max() <= 1e-5
         else:
-            ra = rel_err(alt, got)
-            assert (ra <= 1e-6).mean() >= d["jitter_frac"] - 0.05 and ra.max() <= 3.0 * d["jitter_max"]
+            assert (re <= 1e-6).mean() >= 0.9 and re.max() <= 2e-4
 
 
 @pytest.mark.parametrize("method", ["spg", "brent"])
@@ -347,10 +410,14 @@ def test_fit_cluster_kernel_takes_parked_genes(bn, ctx, oracle, long_sparse, met
     d = long_sparse
     M = bn.Check_input(d["X"], ctx)
     kw = dict(SIZE_lower=d["lo"], SIZE_upper=d["hi"], return_info=True, method=method)
-    ref, conv_r, nfe_r = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], **kw)
-    assert ctx.last_fit()["parked"] == 0
-    got, conv, nfe = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], park_after=6, **kw)
-    info = ctx.last_fit()
+    ctx.tune(bn.api.TUNE_FIT_VARIANT, 3)        # the first-generation sweep kernel (version 2 parks nothing)
+    try:
+        ref, conv_r, nfe_r = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], **kw)
+        assert ctx.last_fit()["parked"] == 0
+        got, conv, nfe = bn.BB_Fun(M, d["beta"], d["mu0"], d["s0"], park_after=6, **kw)
+        info = ctx.last_fit()
+    finally:
+        ctx.tune(bn.api.TUNE_FIT_VARIANT, 0)
     assert info["variant"] == 3 and info["park_after"] == 6
     assert info["parked"] >= 0.5 * int((nfe_r > 6).sum()) > 0, info
     assert np.array_equal(conv, conv_r)
