@@ -39,6 +39,7 @@ class PriorOut(C.Structure):
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p)
 TILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
+GROUP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/baynorm_b200.h declares
 _VP, _I64, _I32, _D, _U64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64
@@ -93,6 +94,19 @@ SIGNATURES = {
     "bn_csc_result_to_mat": (C.c_int, [_VP, _VP, C.POINTER(_VP)]),
     "bn_csc_result_free": (None, [_VP]),
     "bn_post_stream": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _U64, _I64, TILE_SINK, _VP]),
+    "bn_group_create": (C.c_int, [C.c_int, _VP, C.POINTER(_VP)]),
+    "bn_group_destroy": (None, [_VP]),
+    "bn_group_last_error": (C.c_char_p, [_VP]),
+    "bn_group_size": (C.c_int, [_VP]),
+    "bn_group_ctx": (_VP, [_VP, C.c_int]),
+    "bn_group_run": (C.c_int, [_VP, GROUP_FN, _VP]),
+    "bn_group_mat_from_csc": (C.c_int, [_VP, _I64, _I64, _VP, C.c_int, _VP, _VP, C.POINTER(_VP)]),
+    "bn_gmat_free": (None, [_VP]),
+    "bn_gmat_bounds": (C.c_int, [_VP, _VP]),
+    "bn_gmat_shard": (_VP, [_VP, C.c_int]),
+    "bn_group_beta_default": (C.c_int, [_VP, _VP, _D, _VP]),
+    "bn_group_prior": (C.c_int, [_VP, _VP, _VP, C.c_int, C.POINTER(FitOpts), C.POINTER(PriorOut)]),
+    "bn_group_post": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP, _I64, _I64, C.c_int, _U64, _VP]),
     "bn_debug_last_fit": (C.c_int, [_VP, C.POINTER(_I64)]),
     "bn_debug_dense_table": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_double, _VP, C.c_int64, _VP]),
     "bn_debug_tune": (C.c_int, [_VP, C.c_int, C.c_int]),

@@ -454,6 +454,106 @@ def SyntheticControl(Data, BETA_vec, seed=None, ctx=None):
 
 
 # --------------------------------------------------------------------------------------
+# one process, several GPUs (bn_group): what `parallel = TRUE, NCores = n` is to the reference
+# (R/PRIOR_FUNCTIONS.R:426-427), with gene blocks resident on the devices instead of a SOCK cluster
+# --------------------------------------------------------------------------------------
+class DeviceGroup:
+    """ndev GPUs driven from this process; collectives over NCCL inside the library (bn_group_create)."""
+
+    def __init__(self, ndev, devices=None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        dv = (C.c_int * ndev)(*devices) if devices is not None else None
+        rc = self.lib.bn_group_create(int(ndev), dv, C.byref(h))
+        if rc != 0:
+            raise BayNormError(rc, self.lib.bn_group_last_error(None).decode())
+        self.h, self.ndev, self._mats = h, int(ndev), []
+
+    def check(self, rc):
+        if rc != 0:
+            raise BayNormError(rc, self.lib.bn_group_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            for gm in self._mats:
+                gm.close()
+            self.lib.bn_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def matrix(self, Data):
+        """dgCMatrix-like (scipy sparse / dense array) -> gene blocks resident on the devices."""
+        import scipy.sparse as sp
+        A = Data.tocsc(copy=True) if sp.issparse(Data) else sp.csc_matrix(np.asarray(Data, dtype=_F64))
+        A.sum_duplicates()
+        A.sort_indices()
+        G, Cn = A.shape
+        p, i, x = np.ascontiguousarray(A.indptr, np.int64), np.ascontiguousarray(A.indices, np.int32), np.ascontiguousarray(A.data, _F64)
+        h = C.c_void_p()
+        self.check(self.lib.bn_group_mat_from_csc(self.h, G, Cn, _ptr(p), 1, _ptr(i), _ptr(x), C.byref(h)))
+        gm = GroupMatrix(self, h, G, Cn)
+        self._mats.append(gm)
+        return gm
+
+    def beta_default(self, gm, mean_beta=0.06):
+        beta = np.zeros(gm.C, _F64)
+        self.check(self.lib.bn_group_beta_default(self.h, gm.h, float(mean_beta), _ptr(beta)))
+        return beta
+
+    def Prior_fun(self, gm, BETA_vec, BB_SIZE=True, GR=False, method="spg"):
+        """Prior_fun(FIX_MU = TRUE) over the group: the dict of api.Prior_fun(return_info=True)."""
+        b = _vec(BETA_vec, gm.C, "BETA_vec")
+        G = gm.G
+        MU, SIZE = np.zeros(G, _F64), np.zeros(G, _F64)
+        BB, ADJ = (np.zeros(G, _F64), np.zeros(G, _F64)) if BB_SIZE else (None, None)
+        conv, nfe = np.zeros(G, np.int32), np.zeros(G, np.int32)
+        po = PriorOut()
+        po.MME_MU, po.MME_SIZE = _ptr(MU), _ptr(SIZE)
+        po.BB_SIZE, po.MME_SIZE_adjust = _ptr(BB), _ptr(ADJ)
+        po.conv, po.nfeval = _ptr(conv), _ptr(nfe)
+        o = _fit_opts(GR, method)
+        self.check(self.lib.bn_group_prior(self.h, gm.h, _ptr(b), 1 if BB_SIZE else 0, C.byref(o), C.byref(po)))
+        out = {"MME_prior": {"MME_MU": MU, "MME_SIZE": SIZE}, "BETA_vec": b}
+        if BB_SIZE:
+            out["BB_prior"] = {"BB_SIZE": BB, "MME_MU": MU}
+            out["MME_SIZE_adjust"] = ADJ
+        out["_info"] = {"conv": conv, "nfeval": nfe, "size_lower": po.size_lower, "size_upper": po.size_upper,
+                        "coef": tuple(po.coef), "seconds": tuple(po.seconds)}
+        return out
+
+    def posterior(self, kind, gm, BETA_vec, size, mu, S=20, seed=0, col0=0, ncol=None):
+        """kind: "mean" | "mode" | "sample" -> G x ncol (x S) array, Fortran order like the reference's mat / cube."""
+        k = {"mean": 0, "mode": 1, "sample": 2}[kind]
+        ncol = gm.C - col0 if ncol is None else ncol
+        b, sz, mm = _vec(BETA_vec, gm.C, "BETA_vec"), _vec(size, gm.G, "size"), _vec(mu, gm.G, "mu")
+        shape = (gm.G, ncol, S) if k == 2 else (gm.G, ncol)
+        out = np.zeros(shape, _F64, order="F")
+        self.check(self.lib.bn_group_post(self.h, gm.h, k, _ptr(b), _ptr(sz), _ptr(mm), int(col0), int(ncol), int(S),
+                                          C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(out)))
+        return out
+
+
+class GroupMatrix:
+    def __init__(self, group, handle, G, Cn):
+        self.group, self.h, self.G, self.C = group, handle, int(G), int(Cn)
+
+    def bounds(self):
+        b = np.zeros(self.group.ndev + 1, np.int64)
+        self.group.check(self.group.lib.bn_gmat_bounds(self.h, _ptr(b)))
+        return b
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.group.lib.bn_gmat_free(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------------------
 # R-level functions
 # --------------------------------------------------------------------------------------
 TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS, TUNE_SAMPLE_SERIAL = 0, 1, 2, 3

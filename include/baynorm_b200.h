@@ -265,6 +265,37 @@ BN_API int bn_beta_fun(bn_ctx *ctx, bn_mat *m, double MeanBETA, double *BETA, in
 BN_API int bn_synthetic_control(bn_ctx *ctx, bn_mat *m, const double *BETA_vec, uint64_t seed, double *lambda,
                                 double *N_c);
 
+/* ---- one process, several GPUs  (SURVEY.md 8(b) "Threading", 8(e)) ------------------------ */
+/* A context per device whose gene-sharded collectives run over NCCL (ncclCommInitAll; libnccl.so.2 is loaded with dlopen on
+ * the first call, never linked), plus group versions of the entry points an R session calls.  Stands where the reference
+ * starts a SOCK cluster over genes (R/PRIOR_FUNCTIONS.R:426-427, parallel = TRUE): there every worker receives the whole
+ * matrix; here device k holds the gene block [bounds[k], bounds[k+1]).  devices = NULL: 0 .. ndev-1.  The group entry points
+ * take HOST pointers and run one host thread per device; results are those of the one-device path (tested bit for bit). */
+typedef struct bn_group bn_group;
+typedef struct bn_gmat bn_gmat; /* a matrix split into gene blocks, block k resident on device k */
+BN_API int bn_group_create(int ndev, const int *devices, bn_group **out);
+BN_API void bn_group_destroy(bn_group *g);
+BN_API const char *bn_group_last_error(const bn_group *g); /* g may be NULL: last creation error of this thread */
+BN_API int bn_group_size(const bn_group *g);
+BN_API bn_ctx *bn_group_ctx(bn_group *g, int k);
+/* fn(user, k, context k) on one host thread per device, all at once (whatever fn calls may use the collectives); returns
+ * the largest status code. */
+typedef int (*bn_group_fn)(void *user, int k, bn_ctx *ctx);
+BN_API int bn_group_run(bn_group *g, bn_group_fn fn, void *user);
+/* dgCMatrix in (host arrays, see bn_mat_from_csc); contiguous gene blocks balanced on C + 4 nnz_gene. */
+BN_API int bn_group_mat_from_csc(bn_group *g, int64_t G, int64_t C, const void *p, int p_is_int64, const int32_t *i,
+                                 const double *x, bn_gmat **out);
+BN_API void bn_gmat_free(bn_gmat *gm);
+BN_API int bn_gmat_bounds(const bn_gmat *gm, int64_t *bounds /* [ndev + 1] */);
+BN_API bn_mat *bn_gmat_shard(bn_gmat *gm, int k);
+/* bn_beta_default / bn_prior / bn_post_{mean,mode,sample} over the group: per-gene arrays are full length G, `out` of
+ * bn_group_post is the full column-major G x ncol (x S) host array (kind: 0 mean, 1 mode, 2 S draws). */
+BN_API int bn_group_beta_default(bn_group *g, bn_gmat *gm, double mean_beta, double *beta);
+BN_API int bn_group_prior(bn_group *g, bn_gmat *gm, const double *BETA_vec, int BB_SIZE, const bn_fit_opts *opts,
+                          bn_prior_out *out);
+BN_API int bn_group_post(bn_group *g, bn_gmat *gm, int kind, const double *BETA_vec, const double *size, const double *mu,
+                         int64_t col0, int64_t ncol, int S, uint64_t seed, double *out);
+
 /* ---- benchmarking helpers ---------------------------------------------------------- */
 /* Forget the gene-major twin of the matrix so the next per-gene stage rebuilds it (bench.py
  * times the build inside every step). */

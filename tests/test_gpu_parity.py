@@ -1286,3 +1286,55 @@ def test_cuda_against_reference_golden(bn, ctx):
     d = bn.Main_NB_Bay(M, beta, size, mu, S=2000, seed=1)
     z = (d.mean(2) - R["Main_NB_Bay_mean_over_2000"]) / np.sqrt((d.var(2, ddof=1) + R["Main_NB_Bay_var_over_2000"]) / 2000 + 1e-12)
     assert np.abs(z).max() < 6.0                                                                         # two-sample z per element
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one process, several devices (bn_group): the library's own threads + NCCL instead of one process per GPU
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_count():
+    import ctypes as CT
+    try:
+        rt = CT.CDLL("libcudart.so.12")
+    except OSError:
+        rt = CT.CDLL("libcudart.so")
+    n = CT.c_int(0)
+    return n.value if rt.cudaGetDeviceCount(CT.byref(n)) == 0 else 0
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_device_group_matches_one_device(bn, ctx, small, ndev):
+    """bn_group_*: gene blocks on ndev devices driven by one host thread each, collectives over NCCL loaded inside the
+    library (R/PRIOR_FUNCTIONS.R:426-427 is the reference's parallel branch).  BETA, MME and BB_SIZE equal the one-device
+    run bit for bit, the adjusted size to a few ulps (its five OLS sums are added in another order); posterior mean,
+    mode and draws are bit-identical (draws are pure functions of seed, gene, cell and plane)."""
+    if _device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    from baynorm_b200.api import DeviceGroup
+    X = small["X"]
+    M1 = bn.Check_input(X, ctx)
+    beta1 = bn.api._default_beta(M1)
+    full = bn.Prior_fun(M1, beta1, verbose=False, return_info=True)
+    grp = DeviceGroup(ndev)
+    try:
+        gm = grp.matrix(X)
+        b = gm.bounds()
+        assert b[0] == 0 and b[-1] == X.shape[0] and np.all(np.diff(b) > 0)
+        beta = grp.beta_default(gm)
+        assert np.array_equal(beta, beta1)
+        P = grp.Prior_fun(gm, beta)
+        assert np.array_equal(P["MME_prior"]["MME_MU"], full["MME_prior"]["MME_MU"])
+        assert np.array_equal(P["MME_prior"]["MME_SIZE"], full["MME_prior"]["MME_SIZE"])
+        assert np.array_equal(P["BB_prior"]["BB_SIZE"], full["BB_prior"]["BB_SIZE"])
+        assert np.array_equal(P["_info"]["conv"], full["_info"]["conv"])
+        assert rel_err(P["MME_SIZE_adjust"], full["MME_SIZE_adjust"]).max() < 1e-12
+        assert P["_info"]["size_lower"] == full["_info"]["size_lower"] and P["_info"]["size_upper"] == full["_info"]["size_upper"]
+        size, mu = full["MME_SIZE_adjust"], full["MME_prior"]["MME_MU"]
+        c0, nc = 7, 300
+        mean = grp.posterior("mean", gm, beta, size, mu, col0=c0, ncol=nc)
+        mode = grp.posterior("mode", gm, beta, size, mu, col0=c0, ncol=nc)
+        draws = grp.posterior("sample", gm, beta, size, mu, S=5, seed=77, col0=c0, ncol=nc)
+        assert np.array_equal(mean, bn.Main_mean_NB_Bay(M1, beta, size, mu, ctx=ctx, col0=c0, ncol=nc))
+        assert np.array_equal(mode, bn.Main_mode_NB_Bay(M1, beta, size, mu, ctx=ctx, col0=c0, ncol=nc))
+        assert np.array_equal(draws, bn.Main_NB_Bay(M1, beta, size, mu, S=5, seed=77, ctx=ctx, col0=c0, ncol=nc))
+    finally:
+        grp.close()
