@@ -36,6 +36,61 @@ static bn_ctx *ctx(void)
     return g_ctx;
 }
 
+/* Several GPUs from this R session (bnb_set_devices(n), called by the patched Prior_fun / bayNorm when
+ * options(bayNorm.b200.devices = n) is set): the stand-in for the reference's SOCK cluster (R/PRIOR_FUNCTIONS.R:426-427).
+ * The prior and the dense posterior routines then run over gene blocks on n devices (bn_group_*). */
+static bn_group *g_group = NULL;
+
+static void check_group(int rc)
+{
+    if (rc == BN_ERR_BETA_RANGE) Rf_error("The range of BETA must be within (0,1).");
+    if (rc != BN_OK) Rf_error("baynorm_b200 (%d): %s", rc, bn_group_last_error(g_group));
+}
+
+SEXP bnb_set_devices(SEXP n)
+{
+    const int want = Rf_asInteger(n); /* NA_INTEGER is INT_MIN: rejected below */
+    if (want < 1) Rf_error("the number of devices must be a positive integer");
+    if (g_group && bn_group_size(g_group) != want) {
+        bn_group_destroy(g_group);
+        g_group = NULL;
+    }
+    if (want > 1 && !g_group) {
+        int rc = bn_group_create(want, NULL, &g_group);
+        if (rc != BN_OK) Rf_error("baynorm_b200 (%d): %s", rc, bn_group_last_error(NULL));
+    }
+    return Rf_ScalarInteger(g_group ? bn_group_size(g_group) : 1);
+}
+
+static void gmat_finalizer(SEXP p)
+{
+    bn_gmat *m = (bn_gmat *)R_ExternalPtrAddr(p);
+    if (m) bn_gmat_free(m);
+    R_ClearExternalPtr(p);
+}
+
+/* dgCMatrix -> external pointer holding the gene-sharded matrix of the current group.  Caller PROTECTs the result. */
+static SEXP upload_group(SEXP Data, int64_t *G_out, int64_t *C_out)
+{
+    SEXP i = PROTECT(Rf_coerceVector(R_do_slot(Data, Rf_install("i")), INTSXP));
+    SEXP p = PROTECT(Rf_coerceVector(R_do_slot(Data, Rf_install("p")), INTSXP));
+    SEXP x = PROTECT(Rf_coerceVector(R_do_slot(Data, Rf_install("x")), REALSXP));
+    SEXP dim = PROTECT(Rf_coerceVector(R_do_slot(Data, Rf_install("Dim")), INTSXP));
+    if (XLENGTH(dim) != 2) Rf_error("Data@Dim must have length 2");
+    const int G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    if (XLENGTH(p) != (R_xlen_t)C + 1) Rf_error("Data@p has length %ld, expected %d", (long)XLENGTH(p), C + 1);
+    if (XLENGTH(i) != XLENGTH(x) || XLENGTH(i) < INTEGER(p)[C]) Rf_error("Data@i / Data@x shorter than Data@p[ncol + 1]");
+    SEXP ext = PROTECT(R_MakeExternalPtr(NULL, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ext, gmat_finalizer, TRUE);
+    bn_gmat *m = NULL;
+    check_group(bn_group_mat_from_csc(g_group, G, C, INTEGER(p), 0, INTEGER(i), REAL(x), &m));
+    R_SetExternalPtrAddr(ext, m);
+    *G_out = G;
+    *C_out = C;
+    UNPROTECT(5);
+    return ext;
+}
+
 static void check(int rc)
 {
     if (rc == BN_ERR_BETA_RANGE) Rf_error("The range of BETA must be within (0,1)."); /* R/bayNorm.r:185-187 */
@@ -117,6 +172,20 @@ static SEXP new_dgCMatrix(int nrow, int ncol, SEXP i, SEXP p, SEXP x)
  * thres is unused upstream as well (:1067, :1148, :1230). */
 static SEXP posterior(SEXP Data, SEXP BETA_vec, SEXP size, SEXP mu, SEXP S, int kind)
 {
+    if (g_group) { /* gene blocks over the devices of the group */
+        int64_t G, C;
+        SEXP gext = PROTECT(upload_group(Data, &G, &C));
+        SEXP b = PROTECT(as_real(BETA_vec, "BETA_vec", C)), sz = PROTECT(as_real(size, "size", G)), m = PROTECT(as_real(mu, "mu", G));
+        const int s = kind == 2 ? Rf_asInteger(S) : 1;
+        if (s <= 0) Rf_error("S must be a positive integer");
+        SEXP out = PROTECT(kind == 2 ? Rf_alloc3DArray(REALSXP, (int)G, (int)C, s) : Rf_allocMatrix(REALSXP, (int)G, (int)C));
+        int rc = bn_group_post(g_group, (bn_gmat *)R_ExternalPtrAddr(gext), kind, REAL(b), REAL(sz), REAL(m), 0, C, s,
+                               kind == 2 ? seed_from_R() : 0, REAL(out));
+        gmat_finalizer(gext);
+        check_group(rc);
+        UNPROTECT(5);
+        return out;
+    }
     SEXP ext = PROTECT(bnb_upload(Data));
     int64_t info[4];
     bn_mat_info(mat_of(ext), info);
@@ -360,6 +429,28 @@ SEXP bnb_fit_size(SEXP Data, SEXP BETA_vec, SEXP mu0, SEXP size0, SEXP lower, SE
 /* Prior_fun(FIX_MU = TRUE): list(MME_MU, MME_SIZE, BB_SIZE, MME_SIZE_adjust); R assembles the data.frame */
 SEXP bnb_prior(SEXP Data, SEXP BETA_vec, SEXP BB_SIZE, SEXP GR)
 {
+    if (g_group) { /* gene blocks over the devices of the group */
+        int64_t G, C;
+        SEXP gext = PROTECT(upload_group(Data, &G, &C));
+        SEXP b = PROTECT(as_real(BETA_vec, "BETA_vec", C));
+        const int bb = Rf_asLogical(BB_SIZE) == TRUE;
+        SEXP L = PROTECT(Rf_allocVector(VECSXP, 4));
+        for (int k = 0; k < 4; k++) SET_VECTOR_ELT(L, k, Rf_allocVector(REALSXP, (k < 2 || bb) ? G : 0));
+        bn_prior_out po;
+        memset(&po, 0, sizeof(po));
+        po.MME_MU = REAL(VECTOR_ELT(L, 0));
+        po.MME_SIZE = REAL(VECTOR_ELT(L, 1));
+        po.BB_SIZE = bb ? REAL(VECTOR_ELT(L, 2)) : NULL;
+        po.MME_SIZE_adjust = bb ? REAL(VECTOR_ELT(L, 3)) : NULL;
+        bn_fit_opts o;
+        bn_fit_opts_default(&o);
+        o.use_gradient = Rf_asLogical(GR) == TRUE;
+        int rc = bn_group_prior(g_group, (bn_gmat *)R_ExternalPtrAddr(gext), REAL(b), bb, &o, &po);
+        gmat_finalizer(gext);
+        check_group(rc);
+        UNPROTECT(3);
+        return L;
+    }
     SEXP ext = PROTECT(bnb_upload(Data));
     int64_t info[4];
     bn_mat_info(mat_of(ext), info);
@@ -477,6 +568,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"bnb_fit_size_mu", (DL_FUNC)&bnb_fit_size_mu, 7},
     {"bnb_beta_fun", (DL_FUNC)&bnb_beta_fun, 2},
     {"bnb_synthetic_control", (DL_FUNC)&bnb_synthetic_control, 2},
+    {"bnb_set_devices", (DL_FUNC)&bnb_set_devices, 1},
     {NULL, NULL, 0}};
 
 void R_init_bayNorm(DllInfo *dll)
@@ -487,6 +579,8 @@ void R_init_bayNorm(DllInfo *dll)
 
 void R_unload_bayNorm(DllInfo *dll)
 {
+    if (g_group) bn_group_destroy(g_group);
+    g_group = NULL;
     if (g_ctx) bn_ctx_destroy(g_ctx);
     g_ctx = NULL;
 }

@@ -1,6 +1,7 @@
 ## R-side changes a maintainer makes so that BB_Fun / Prior_fun / bayNorm call the batched entries.
 ## Signatures, defaults and return structures are unchanged (R/PRIOR_FUNCTIONS.R:380-384, :241-245,
-## R/bayNorm.r:120-129); `parallel` and `NCores` are accepted and ignored (the fit is one kernel launch).
+## R/bayNorm.r:120-129).  `NCores` is accepted and ignored (the fit is one kernel launch per device); `parallel = TRUE`
+## spreads the genes over options(bayNorm.b200.devices = n) GPUs of this session (default 1) instead of a SOCK cluster.
 ## Not executed in this repository (no R in the image).
 
 BB_Fun <- function(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec,
@@ -24,6 +25,7 @@ BB_Fun <- function(Data, BETA_vec, INITIAL_MU_vec, INITIAL_SIZE_vec,
 Prior_fun <- function(Data, BETA_vec, parallel = TRUE, NCores = 5, FIX_MU = TRUE, GR = FALSE,
                       BB_SIZE = TRUE, verbose = TRUE) {
     Data <- Check_input(Data)
+    .Call("bnb_set_devices", if (parallel) as.integer(getOption("bayNorm.b200.devices", 1L)) else 1L, PACKAGE = "bayNorm")
     r <- .Call("bnb_prior", Data, as.numeric(BETA_vec), BB_SIZE && FIX_MU, GR, PACKAGE = "bayNorm")
     MME_prior <- data.frame(MME_MU = r[[1]], MME_SIZE = r[[2]], row.names = rownames(Data))
     if (!BB_SIZE) return(list(MME_prior = MME_prior, BETA_vec = BETA_vec))

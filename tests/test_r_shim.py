@@ -221,3 +221,43 @@ def test_shim_errors_do_not_leak_device_matrices(R, fixture_data):
     with pytest.raises(RError, match="Data@p has length"):
         R.call("_bayNorm_rowMeansFast", R.lib.rmock_dgC(20, 75, R.integer(np.zeros(75)), R.integer([]), R.real([])))
     R.lib.rmock_run_finalizers()
+
+
+@pytest.mark.gpu
+def test_shim_multi_device_route(R, fixture_data):
+    """bnb_set_devices(n): Prior_fun and the posterior routines over n GPUs of this session (the stand-in for the reference's
+    SOCK cluster, R/PRIOR_FUNCTIONS.R:426-427) return what the one-device route returns.  With one GPU in the box the call
+    must still be accepted for n = 1 and refuse n = 2 as an R error."""
+    import ctypes as CT
+    try:
+        rt = CT.CDLL("libcudart.so.12")
+    except OSError:
+        rt = CT.CDLL("libcudart.so")
+    n = CT.c_int(0)
+    ndev = n.value if rt.cudaGetDeviceCount(CT.byref(n)) == 0 else 0
+    X, beta, size, mu = (fixture_data[k] for k in ("inputdata", "inputbeta", "size", "mu"))
+    D = R.dgC(X)
+    S, thres = R.integer([3]), R.integer([10000000])
+    assert R.value(R.call("bnb_set_devices", R.integer([1])))[0] == 1
+    one = R.value(R.call("bnb_prior", D, R.real(beta), R.lgl(1), R.lgl(0)))
+    mean1 = R.value(R.call("_bayNorm_Main_mean_NB_Bay", D, R.real(beta), R.real(size), R.real(mu), S, thres))
+    if ndev < 2:
+        with pytest.raises(RError):
+            R.call("bnb_set_devices", R.integer([2]))
+        return
+    try:
+        assert R.value(R.call("bnb_set_devices", R.integer([2])))[0] == 2
+        two = R.value(R.call("bnb_prior", D, R.real(beta), R.lgl(1), R.lgl(0)))
+        for k in range(3):
+            assert np.array_equal(one[k], two[k])
+        np.testing.assert_allclose(two[3], one[3], rtol=1e-12)
+        mean2 = R.value(R.call("_bayNorm_Main_mean_NB_Bay", D, R.real(beta), R.real(size), R.real(mu), S, thres))
+        assert np.array_equal(mean1, mean2)
+        R.lib.rmock_set_seed(11)
+        d2 = R.value(R.call("_bayNorm_Main_NB_Bay", D, R.real(beta), R.real(size), R.real(mu), S, thres))
+    finally:
+        R.call("bnb_set_devices", R.integer([1]))
+    R.lib.rmock_set_seed(11)
+    d1 = R.value(R.call("_bayNorm_Main_NB_Bay", D, R.real(beta), R.real(size), R.real(mu), S, thres))
+    assert np.array_equal(d1, d2)
+    assert R.lib.rmock_run_finalizers() == 0
