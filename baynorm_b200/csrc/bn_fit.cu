@@ -923,14 +923,32 @@ __device__ __forceinline__ void nb_loglik2(const FitGene2 &g, const double *phi,
     }
     const double *__restrict__ gs = g.gs;
     const int nm = g.kmax > FIT2_CMAX ? (int)tail[FIT2_CMAX] : g.n_big; // start of the prefix-product section
-    for (int k = nm + tid; k < n; k += 4 * TPG) {
-        const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG;
-        const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
-                     b3 = k3 < n ? __ldg(gs + k3) : 0.0;
-        FIT2_ENTRY(k, b0)
-        FIT2_ENTRY(k1, b1)
-        FIT2_ENTRY(k2, b2)
-        FIT2_ENTRY(k3, b3)
+    if (TPG == 32) {
+        for (int k = nm + tid; k < n; k += 4 * TPG) {
+            const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG;
+            const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
+                         b3 = k3 < n ? __ldg(gs + k3) : 0.0;
+            FIT2_ENTRY(k, b0)
+            FIT2_ENTRY(k1, b1)
+            FIT2_ENTRY(k2, b2)
+            FIT2_ENTRY(k3, b3)
+        }
+    } else {
+        // long genes stream their entries from L2 / HBM: eight loads in flight per thread
+        for (int k = nm + tid; k < n; k += 8 * TPG) {
+            const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG, k4 = k + 4 * TPG, k5 = k + 5 * TPG, k6 = k + 6 * TPG, k7 = k + 7 * TPG;
+            const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
+                         b3 = k3 < n ? __ldg(gs + k3) : 0.0, b4 = k4 < n ? __ldg(gs + k4) : 0.0, b5 = k5 < n ? __ldg(gs + k5) : 0.0,
+                         b6 = k6 < n ? __ldg(gs + k6) : 0.0, b7 = k7 < n ? __ldg(gs + k7) : 0.0;
+            FIT2_ENTRY(k, b0)
+            FIT2_ENTRY(k1, b1)
+            FIT2_ENTRY(k2, b2)
+            FIT2_ENTRY(k3, b3)
+            FIT2_ENTRY(k4, b4)
+            FIT2_ENTRY(k5, b5)
+            FIT2_ENTRY(k6, b6)
+            FIT2_ENTRY(k7, b7)
+        }
     }
 #undef FIT2_ENTRY
 #undef FIT2_FOLD_S

@@ -681,7 +681,7 @@ def main():
     ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="spg", choices=["spg", "brent"])
-    ap.add_argument("--tile-gb", type=float, default=8.0, help="recycled HBM output tile")
+    ap.add_argument("--tile-gb", type=float, default=32.0, help="recycled HBM output tile (a posterior call covers one tile: larger tiles amortise its prologue and let the sampler prepare the next column chunk while one is drawn)")
     ap.add_argument("--e2e-out-gb", type=float, default=48.0, help="result bytes delivered to the host per e2e step and rank")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="profiling A/B switch (bn_debug_tune), e.g. 4=16384; recorded in config.tune")

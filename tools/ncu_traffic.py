@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise .ncu-rep captures into profiles/: a text table of the key metrics per kernel
 (profiles/<name>.summary.txt) and the per-launch DRAM traffic bench.py reports as `roofline.traffic`
-(profiles/r1_traffic.json).
+(profiles/r2_traffic.json; BN_TRAFFIC_JSON names another file).
 
 usage: ncu_traffic.py <config>:<phase>:<kernel-regex>:<report.ncu-rep> ...
 """
@@ -44,7 +44,8 @@ def rows_of(rep):
 
 
 def main():
-    traffic_path = ROOT / "profiles" / "r1_traffic.json"
+    import os
+    traffic_path = ROOT / "profiles" / os.environ.get("BN_TRAFFIC_JSON", "r2_traffic.json")
     traffic = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
     seen = set()
     for spec in sys.argv[1:]:
