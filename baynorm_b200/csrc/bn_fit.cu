@@ -934,7 +934,8 @@ __device__ __forceinline__ void nb_loglik2(const FitGene2 &g, const double *phi,
             FIT2_ENTRY(k3, b3)
         }
     } else {
-        // long genes stream their entries from L2 / HBM: eight loads in flight per thread
+        // long genes stream their entries from L2 / HBM: eight loads in flight per thread (a cp.async ring with 24 in flight
+        // measured the same: 170 ms on config 5 either way)
         for (int k = nm + tid; k < n; k += 8 * TPG) {
             const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG, k4 = k + 4 * TPG, k5 = k + 5 * TPG, k6 = k + 6 * TPG, k7 = k + 7 * TPG;
             const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
@@ -1040,14 +1041,41 @@ __device__ __forceinline__ void nb_loglik2(const FitGene2 &g, const double *phi,
 
 // gene lists of the two geometries: warp per gene below FIT2_SPLIT stored entries, CTA per gene from there on
 #define FIT2_SPLIT 4096
-__global__ void __launch_bounds__(256) k_fit2_lists(int64_t G, const int64_t *__restrict__ rowptr, int split, int32_t *__restrict__ small,
-                                                    int32_t *__restrict__ big, unsigned int *__restrict__ counts)
+// One CTA.  Both lists come out longest gene first (128 length classes, a quarter of an octave each; the order inside a class
+// is left to the atomics -- it only decides which group fits a gene): the queue then schedules longest-processing-time
+// first, so the phase does not end on a 1.3 M-entry gene that happened to sit late in the list (gene blocks of 4125 genes:
+// fit 41 - 109 ms over 8 ranks before this).
+__global__ void __launch_bounds__(1024) k_fit2_lists(int64_t G, const int64_t *__restrict__ rowptr, int split, int32_t *__restrict__ small,
+                                                     int32_t *__restrict__ big, unsigned int *__restrict__ counts)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    const bool isbig = rowptr[g + 1] - rowptr[g] >= split;
-    const unsigned slot = atomicAdd(counts + (isbig ? 1 : 0), 1u);
-    (isbig ? big : small)[slot] = (int32_t)g;
+    __shared__ unsigned int hist[2][128], start[2][128];
+    for (int q = threadIdx.x; q < 256; q += 1024) (&hist[0][0])[q] = 0;
+    __syncthreads();
+    auto cls = [](int64_t n) -> int { // descending: class 0 holds the longest genes
+        if (n < 4) return 127;
+        const int e = 63 - __clzll((long long)n);
+        const int c = 4 * e + (int)((n >> (e - 2)) & 3);
+        return c > 127 ? 0 : 127 - c;
+    };
+    for (int64_t g = threadIdx.x; g < G; g += 1024) {
+        const int64_t n = rowptr[g + 1] - rowptr[g];
+        atomicAdd(&hist[n >= split ? 1 : 0][cls(n)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned int acc = 0;
+        for (int c = 0; c < 128; c++) {
+            start[threadIdx.x][c] = acc;
+            acc += hist[threadIdx.x][c];
+        }
+        counts[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int64_t g = threadIdx.x; g < G; g += 1024) {
+        const int64_t n = rowptr[g + 1] - rowptr[g];
+        const int w = n >= split ? 1 : 0;
+        (w ? big : small)[atomicAdd(&start[w][cls(n)], 1u)] = (int32_t)g;
+    }
 }
 
 // spg asks for -l(p) and then, unless the line search rejects p, for -l(p + eps) (its forward-difference gradient): both are
@@ -1957,7 +1985,7 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
                   tails.p);
         int32_t *l_small = lists.p, *l_big = lists.p + G;
         const int split = ctx->tune[BN_TUNE_FIT_SPLIT] > 0 ? ctx->tune[BN_TUNE_FIT_SPLIT] : FIT2_SPLIT;
-        BN_LAUNCH(ctx, k_fit2_lists, (unsigned)((G + 255) / 256), 256, 0, G, m->rowptr, split, l_small, l_big, cnt2.p);
+        BN_LAUNCH(ctx, k_fit2_lists, 1, 1024, 0, G, m->rowptr, split, l_small, l_big, cnt2.p);
 #define FIT2_ARGS(L, K, Q) L, cnt2.p + K, m->C, m->rowptr, m->gm, gs.p, gx.p, gmeta.p, tails.p, d_beta, d_mu0, d_size0, params.p, coef, meta, o, q2.p + Q, \
     d_size_out, d_conv, d_nfe
         // the long genes first: their tail is what ends the phase

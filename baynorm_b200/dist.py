@@ -20,15 +20,16 @@ import numpy as np
 _OPS = {0: "SUM", 1: "MIN", 2: "MAX"}
 
 
-def balanced_gene_blocks(row_nnz, world, n_cells=0):
+def balanced_gene_blocks(row_nnz, world, n_cells=0, nnz_weight=4.0):
     """Contiguous gene blocks with near-equal cost.  Fit cost per gene ~ n_cells (dense zero
     term) + c * nnz_gene, posterior cost ~ n_cells; expression is heavy-tailed, so blocks are
-    balanced on (n_cells + 4 * nnz_gene) instead of on gene count.  Returns world+1 boundaries."""
+    balanced on (n_cells + nnz_weight * nnz_gene) instead of on gene count (4: dense matrices with the
+    first-generation fit; ~1.5: sparse matrices with fit version 2 and S = 20 draws).  Returns world+1 boundaries."""
     row_nnz = np.asarray(row_nnz, dtype=np.float64)
     G = row_nnz.shape[0]
     if world <= 1:
         return np.array([0, G], dtype=np.int64)
-    cost = np.cumsum(float(n_cells) + 4.0 * row_nnz)
+    cost = np.cumsum(float(n_cells) + float(nnz_weight) * row_nnz)
     total = cost[-1]
     bounds = [0]
     for k in range(1, world):

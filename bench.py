@@ -224,7 +224,16 @@ def run_ours(args):
     Gt, C, S, groups = cfg["G"], cfg["C"], cfg["S"], cfg["groups"]
     strong = args.config == 5 and not args.weak          # config 5: ONE matrix, gene blocks of G / N
     if strong:
-        bounds = [(Gt * k) // world for k in range(world + 1)]
+        if world > 1:
+            # gene blocks of equal COST, not equal size: the posterior costs ~C per gene, the prior (gene-major build, moments,
+            # fit version 2) ~1.5 per stored entry (measured on config 5: 83 us per gene and 0.093 ns per entry); the entries of a
+            # gene are estimated from the generator's parameters (P(x > 0) at the mean BETA) -- expression is heavy-tailed, so
+            # blocks of equal size differ 2.6x in entries (fit 41 - 109 ms over 8 ranks before this)
+            mu_g, size_g, beta_g = synth_params(Gt, C, cfg["m0"])
+            nnz_g = C * (1.0 - (size_g / (size_g + mu_g * beta_g.mean())) ** size_g)
+            bounds = [int(b) for b in bdist.balanced_gene_blocks(nnz_g, world, n_cells=C, nnz_weight=1.5)]
+        else:
+            bounds = [0, Gt]
         g0, G = bounds[rank], bounds[rank + 1] - bounds[rank]
         G_total = Gt
     else:
