@@ -711,6 +711,9 @@ struct GeneMeta2 {
     int n_big;    // stored entries with x > FIT2_HMAX
 };
 
+#define FIT2_RW 8   // entries (four pairs) a thread of the CTA kernel copies per round
+#define FIT2_NST 4  // rounds of its shared-memory ring
+#define FIT2_RING_BYTES (FIT2_NST * FIT2_RW * 256 * 8)
 #define FIT2_NK (FIT2_HMAX + 2) // sort keys: 0 (explicitly stored zero: dropped), 1..HMAX, HMAX + 1 (larger counts)
 
 // Staging, CTA per gene (atomic queue): a counting sort of the gene's stored entries by count, DESCENDING -- entries with
@@ -821,6 +824,7 @@ __global__ void __launch_bounds__(256) k_fit2_stage(int64_t G, const int64_t *__
 struct FitGene2 {
     const double *gs;     // staged entries of the gene
     const uint8_t *gx;    // their counts - 1 (entries up to FIT2_HMAX)
+    double *ring;         // CTA kernel: FIT2_RING_BYTES of shared memory
     const uint32_t *tail; // shared memory: tail[k] = #{x > k}, k <= FIT2_HMAX
     double mu, Kc;
     int kmax, n_big;
@@ -923,33 +927,88 @@ __device__ __forceinline__ void nb_loglik2(const FitGene2 &g, const double *phi,
     }
     const double *__restrict__ gs = g.gs;
     const int nm = g.kmax > FIT2_CMAX ? (int)tail[FIT2_CMAX] : g.n_big; // start of the prefix-product section
+    // A round whose entries all carry the current count and whose factors fit the exponent budget -- nearly every round of a
+    // long gene -- needs none of the per-entry tests: RW fused multiply-adds and a product tree per trial size.
     if (TPG == 32) {
         for (int k = nm + tid; k < n; k += 4 * TPG) {
             const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG;
             const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
                          b3 = k3 < n ? __ldg(gs + k3) : 0.0;
-            FIT2_ENTRY(k, b0)
-            FIT2_ENTRY(k1, b1)
-            FIT2_ENTRY(k2, b2)
-            FIT2_ENTRY(k3, b3)
+            if (k3 < nextb && eS + 4 * ub <= 1000) {
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    S[p] *= (fma(r[p], b0, 1.0) * fma(r[p], b1, 1.0)) * (fma(r[p], b2, 1.0) * fma(r[p], b3, 1.0));
+                eS += 4 * ub;
+            } else {
+                FIT2_ENTRY(k, b0)
+                FIT2_ENTRY(k1, b1)
+                FIT2_ENTRY(k2, b2)
+                FIT2_ENTRY(k3, b3)
+            }
         }
     } else {
-        // long genes stream their entries from L2 / HBM: eight loads in flight per thread (a cp.async ring with 24 in flight
-        // measured the same: 170 ms on config 5 either way)
-        for (int k = nm + tid; k < n; k += 8 * TPG) {
-            const int k1 = k + TPG, k2 = k + 2 * TPG, k3 = k + 3 * TPG, k4 = k + 4 * TPG, k5 = k + 5 * TPG, k6 = k + 6 * TPG, k7 = k + 7 * TPG;
-            const double b0 = __ldg(gs + k), b1 = k1 < n ? __ldg(gs + k1) : 0.0, b2 = k2 < n ? __ldg(gs + k2) : 0.0,
-                         b3 = k3 < n ? __ldg(gs + k3) : 0.0, b4 = k4 < n ? __ldg(gs + k4) : 0.0, b5 = k5 < n ? __ldg(gs + k5) : 0.0,
-                         b6 = k6 < n ? __ldg(gs + k6) : 0.0, b7 = k7 < n ? __ldg(gs + k7) : 0.0;
-            FIT2_ENTRY(k, b0)
-            FIT2_ENTRY(k1, b1)
-            FIT2_ENTRY(k2, b2)
-            FIT2_ENTRY(k3, b3)
-            FIT2_ENTRY(k4, b4)
-            FIT2_ENTRY(k5, b5)
-            FIT2_ENTRY(k6, b6)
-            FIT2_ENTRY(k7, b7)
+        // Long genes stream their entries from L2 / HBM (config 5: 830 KB per gene and pass).  Every thread keeps FIT2_NST - 1
+        // rounds of four entry PAIRS in flight through its own column of a shared-memory ring (cp.async, 16 bytes each; a
+        // thread only ever reads what it copied itself, so cp.async.wait_group is the only synchronisation).  With the loads
+        // of a round issued only after the previous round was consumed, every round exposed one DRAM latency (long-scoreboard
+        // stall 12 cycles per issued instruction); 8-byte copies were bound by the load/store unit's queue instead.
+        // Pairs start at an even absolute position (16-byte alignment): an odd first entry goes to thread 0 ahead of its pairs.
+        const int nm2 = nm + (int)((reinterpret_cast<uintptr_t>(gs + nm) >> 3) & 1);
+        if (nm2 > nm && tid == 0) FIT2_ENTRY(nm, __ldg(gs + nm))
+        double2 *rg = reinterpret_cast<double2 *>(g.ring) + tid; // pair i of stage s at rg[(s * 4 + i) * TPG]
+        const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(rg);
+        const double2 *src = reinterpret_cast<const double2 *>(gs + nm2) + tid;
+        int kis = nm2 + 2 * tid, sti = 0, stc = 0; // first entry of the thread's first pair in the next round to issue
+#define FIT2_ISSUE()                                                                                                     \
+    {                                                                                                                    \
+        const uint32_t dst_ = ring0 + (uint32_t)sti * (4 * TPG * 16);                                                    \
+        if (kis + 6 * TPG + 1 < n) {                                                                                     \
+            _Pragma("unroll") for (int i = 0; i < 4; i++)                                                                \
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + i * (TPG * 16)), "l"(src + i * TPG) : "memory"); \
+        } else if (kis < n) {                                                                                            \
+            _Pragma("unroll") for (int i = 0; i < 4; i++)                                                                \
+            {                                                                                                            \
+                const int e0_ = kis + 2 * i * TPG;                                                                       \
+                if (e0_ + 1 < n)                                                                                         \
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + i * (TPG * 16)), "l"(src + i * TPG) : "memory"); \
+                else if (e0_ < n)                                                                                        \
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_ + i * (TPG * 16)), "l"(src + i * TPG) : "memory"); \
+            }                                                                                                            \
+        }                                                                                                                \
+        asm volatile("cp.async.commit_group;" ::: "memory");                                                             \
+        src += 4 * TPG;                                                                                                  \
+        kis += 8 * TPG;                                                                                                  \
+        sti = sti + 1 == FIT2_NST ? 0 : sti + 1;                                                                         \
+    }
+#pragma unroll
+        for (int q = 0; q < FIT2_NST - 1; q++) FIT2_ISSUE()
+        for (int k = nm2 + 2 * tid; k < n; k += 8 * TPG) {
+            FIT2_ISSUE()
+            asm volatile("cp.async.wait_group %0;" ::"n"(FIT2_NST - 1) : "memory");
+            const double2 *st = rg + stc * (4 * TPG);
+            stc = stc + 1 == FIT2_NST ? 0 : stc + 1;
+            const double2 v0 = st[0], v1 = st[TPG], v2 = st[2 * TPG], v3 = st[3 * TPG];
+            const int kl = k + 6 * TPG + 1; // the round's last entry
+            if (kl < nextb && eS + 8 * ub <= 1000) {
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    S[p] *= ((fma(r[p], v0.x, 1.0) * fma(r[p], v0.y, 1.0)) * (fma(r[p], v1.x, 1.0) * fma(r[p], v1.y, 1.0))) *
+                            ((fma(r[p], v2.x, 1.0) * fma(r[p], v2.y, 1.0)) * (fma(r[p], v3.x, 1.0) * fma(r[p], v3.y, 1.0)));
+                eS += 8 * ub;
+            } else {
+                const int e1 = k + 2 * TPG, e2 = k + 4 * TPG, e3 = k + 6 * TPG;
+                FIT2_ENTRY(k, v0.x)
+                FIT2_ENTRY(k + 1, v0.y)
+                FIT2_ENTRY(e1, v1.x)
+                FIT2_ENTRY(e1 + 1, v1.y)
+                FIT2_ENTRY(e2, v2.x)
+                FIT2_ENTRY(e2 + 1, v2.y)
+                FIT2_ENTRY(e3, v3.x)
+                FIT2_ENTRY(e3 + 1, v3.y)
+            }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef FIT2_ISSUE
     }
 #undef FIT2_ENTRY
 #undef FIT2_FOLD_S
@@ -1092,6 +1151,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
            const DenseMeta *__restrict__ meta, FitOpts o, unsigned long long *__restrict__ queue, double *__restrict__ size_out,
            int32_t *__restrict__ conv_out, int32_t *__restrict__ nfe_out)
 {
+    extern __shared__ __align__(16) double fit2_ring[]; // CTA kernel only (FIT2_RING_BYTES)
     constexpr int GPC = TPG == 32 ? 4 : 1; // genes in flight per CTA
     const double lower = params[0], upper = params[1], beta_max = params[2];
     __shared__ BnLogEntry tab[BN_LOG_TABLE_N];
@@ -1124,6 +1184,7 @@ __global__ void __launch_bounds__(TPG == 32 ? 128 : TPG, TPG == 32 ? 6 : 3)
         FitGene2 g;
         g.gs = gs + a;
         g.gx = gx + a;
+        g.ring = TPG == 32 ? nullptr : fit2_ring;
         g.tail = tl;
         g.mu = mu0[gi];
         g.kmax = gmv.kmax;
@@ -1990,11 +2051,16 @@ int bn_fit_size_device(bn_ctx *ctx, bn_mat *m, const double *d_beta, const doubl
     d_size_out, d_conv, d_nfe
         // the long genes first: their tail is what ends the phase
         const int grid_big = (int)std::min<int64_t>(G, (int64_t)sms * 3), grid_small = (int)std::min<int64_t>((G + 3) / 4, (int64_t)sms * 6);
+        if (!ctx->fit2_attr_set) { // function attributes are per device: once per context
+            BN_CUDA(ctx, cudaFuncSetAttribute(k_fit2<256, BN_FIT_BRENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT2_RING_BYTES));
+            BN_CUDA(ctx, cudaFuncSetAttribute(k_fit2<256, BN_FIT_SPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT2_RING_BYTES));
+            ctx->fit2_attr_set = true;
+        }
         if (o.method == BN_FIT_BRENT) {
-            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_BRENT>), grid_big, 256, 0, FIT2_ARGS(l_big, 1, 2));
+            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_BRENT>), grid_big, 256, FIT2_RING_BYTES, FIT2_ARGS(l_big, 1, 2));
             BN_LAUNCH(ctx, (k_fit2<32, BN_FIT_BRENT>), grid_small, 128, 0, FIT2_ARGS(l_small, 0, 1));
         } else {
-            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_SPG>), grid_big, 256, 0, FIT2_ARGS(l_big, 1, 2));
+            BN_LAUNCH(ctx, (k_fit2<256, BN_FIT_SPG>), grid_big, 256, FIT2_RING_BYTES, FIT2_ARGS(l_big, 1, 2));
             BN_LAUNCH(ctx, (k_fit2<32, BN_FIT_SPG>), grid_small, 128, 0, FIT2_ARGS(l_small, 0, 1));
         }
 #undef FIT2_ARGS

@@ -35,6 +35,7 @@ struct bn_ctx {
     cudaStream_t aux[5] = {};
     cudaEvent_t ev_aux[12] = {};
     bool sample_attr_set = false;  // function attributes are per device: set once per context
+    bool fit2_attr_set = false;
     // result streaming (bn_stream.cu): a second stream for device -> host copies, two result tiles in flight
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_comp[2] = {}, ev_copy[2] = {};
