@@ -746,21 +746,33 @@ __global__ void __launch_bounds__(256) k_fit2_stage(int64_t G, const int64_t *__
         const int64_t c0 = nnz * warp / 8, c1 = nnz * (warp + 1) / 8;
         double kk = 0.0, xs = 0.0;
         int xm = 0;
-        for (int64_t base = c0; base < c1; base += 32) {
-            const int64_t k = base + lane;
-            int key = -1;
-            if (k < c1) {
-                const uint64_t e0 = __ldg(nz + k);
-                const uint32_t xi = (uint32_t)e0;
-                const double x = (double)xi;
-                kk += x * __ldg(logbeta + (e0 >> 32)) - bn_lfact(x);
-                xs += x;
-                key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
-                xm = max(xm, key);
+        // four batches of 32 entries in flight per warp (packed word, then the gathered log BETA): one batch at a time left the
+        // kernel waiting on memory 27 cycles per issued instruction
+        for (int64_t base = c0; base < c1; base += 128) {
+            uint64_t e[4];
+            double lb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t k = base + 32 * u + lane;
+                e[u] = k < c1 ? __ldg(nz + k) : 0ull;
             }
-            const unsigned same = __match_any_sync(0xffffffffu, key);
-            if (key > 0 && (same & lt) == 0) wh[warp][key] += (uint32_t)__popc(same);
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; u++) lb[u] = (base + 32 * u + lane < c1) ? __ldg(logbeta + (e[u] >> 32)) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int key = -1;
+                if (base + 32 * u + lane < c1) {
+                    const uint32_t xi = (uint32_t)e[u];
+                    const double x = (double)xi;
+                    kk += x * lb[u] - bn_lfact(x);
+                    xs += x;
+                    key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
+                    xm = max(xm, key);
+                }
+                const unsigned same = __match_any_sync(0xffffffffu, key);
+                if (key > 0 && (same & lt) == 0) wh[warp][key] += (uint32_t)__popc(same);
+                __syncwarp();
+            }
         }
         atomicMax(&xmax_sh, xm);
         const double Kbase = bn_group_sum<256>(kk, red8);
@@ -798,25 +810,35 @@ __global__ void __launch_bounds__(256) k_fit2_stage(int64_t G, const int64_t *__
         }
         __syncthreads();
         double *__restrict__ out = gs + a;
-        for (int64_t base = c0; base < c1; base += 32) {
-            const int64_t k = base + lane;
-            int key = -1;
-            uint64_t e0 = 0;
-            if (k < c1) {
-                e0 = __ldg(nz + k);
-                const uint32_t xi = (uint32_t)e0;
-                key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
+        for (int64_t base = c0; base < c1; base += 128) {
+            uint64_t e[4];
+            double bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t k = base + 32 * u + lane;
+                e[u] = k < c1 ? __ldg(nz + k) : 0ull;
             }
-            const unsigned same = __match_any_sync(0xffffffffu, key);
-            const uint32_t pos = key > 0 ? wh[warp][key] : 0u;
-            __syncwarp();
-            if (key > 0) {
-                if ((same & lt) == 0) wh[warp][key] = pos + (uint32_t)__popc(same);
-                const uint32_t at = pos + (uint32_t)__popc(same & lt);
-                out[at] = key <= FIT2_HMAX ? __ldg(beta + (e0 >> 32)) : __longlong_as_double((long long)(a + k));
-                gx[a + at] = (uint8_t)(key <= FIT2_HMAX ? key - 1 : 0); // count - 1 (1..256 in a byte)
+#pragma unroll
+            for (int u = 0; u < 4; u++) bv[u] = (base + 32 * u + lane < c1) ? __ldg(beta + (e[u] >> 32)) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t k = base + 32 * u + lane;
+                int key = -1;
+                if (k < c1) {
+                    const uint32_t xi = (uint32_t)e[u];
+                    key = xi > FIT2_HMAX ? FIT2_HMAX + 1 : (int)xi;
+                }
+                const unsigned same = __match_any_sync(0xffffffffu, key);
+                const uint32_t pos = key > 0 ? wh[warp][key] : 0u;
+                __syncwarp();
+                if (key > 0) {
+                    if ((same & lt) == 0) wh[warp][key] = pos + (uint32_t)__popc(same);
+                    const uint32_t at = pos + (uint32_t)__popc(same & lt);
+                    out[at] = key <= FIT2_HMAX ? bv[u] : __longlong_as_double((long long)(a + k));
+                    gx[a + at] = (uint8_t)(key <= FIT2_HMAX ? key - 1 : 0); // count - 1 (1..256 in a byte)
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
 }

@@ -156,20 +156,24 @@ __device__ __forceinline__ void nz_load(const uint64_t *__restrict__ gm, const i
 // mode 3: as mode 0 but SIZE is the raw quotient m^2/(v-m) without the R-level NaN rule
 //         (what EstPrior_sprcpp / EstPrior_rcpp themselves return)
 // ---------------------------------------------------------------------------------
-template <bool PACKED>
-__global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_t C, const int64_t *__restrict__ rowptr,
+// TPG = 32: warp per gene, genes below `split` stored entries; TPG = 256: CTA per gene, the long ones (a 1.3 M-entry gene on a
+// single warp took 30 of the 41 ms this kernel needed on config 5).  Either way ONE summation order per gene.
+template <bool PACKED, int TPG>
+__global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t split, int64_t G, int64_t C, const int64_t *__restrict__ rowptr,
                                                      const uint64_t *__restrict__ gm, const int32_t *__restrict__ cell,
                                                      const double *__restrict__ rval,
                                                      const double *__restrict__ beta, const double *__restrict__ means_in,
                                                      double *__restrict__ MU, double *__restrict__ SIZE,
                                                      double *__restrict__ V)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    __shared__ double scratch[8];
+    const int lane = TPG == 32 ? (threadIdx.x & 31) : threadIdx.x; // position inside the gene's group
+    const int64_t warp = TPG == 32 ? (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5 : blockIdx.x;
+    const int64_t nwarp = TPG == 32 ? (gridDim.x * (int64_t)blockDim.x) >> 5 : gridDim.x;
     const double n = (double)C;
     for (int64_t g = warp; g < G; g += nwarp) {
         const int64_t a = rowptr[g], b = rowptr[g + 1];
+        if ((b - a >= split) != (TPG != 32)) continue; // the other kernel's gene (uniform over the group)
         double mean;
         if (mode == 2) {
             mean = means_in[g];
@@ -177,39 +181,39 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
             // four independent loads / divisions / partial sums per lane: the loop is latency-bound otherwise
             double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int64_t k = a + lane;
-            for (; k + 96 < b; k += 128) {
+            for (; k + 3 * TPG < b; k += 4 * TPG) {
                 double x0, x1, x2, x3;
                 int c0, c1, c2, c3;
                 nz_load<PACKED>(gm, cell, rval, k, c0, x0);
-                nz_load<PACKED>(gm, cell, rval, k + 32, c1, x1);
-                nz_load<PACKED>(gm, cell, rval, k + 64, c2, x2);
-                nz_load<PACKED>(gm, cell, rval, k + 96, c3, x3);
+                nz_load<PACKED>(gm, cell, rval, k + TPG, c1, x1);
+                nz_load<PACKED>(gm, cell, rval, k + 2 * TPG, c2, x2);
+                nz_load<PACKED>(gm, cell, rval, k + 3 * TPG, c3, x3);
                 if (beta) {
                     const double b0 = __ldg(beta + c0), b1 = __ldg(beta + c1), b2 = __ldg(beta + c2), b3 = __ldg(beta + c3);
                     x0 = __ddiv_rn(x0, b0), x1 = __ddiv_rn(x1, b1), x2 = __ddiv_rn(x2, b2), x3 = __ddiv_rn(x3, b3);
                 }
                 s += x0, s1 += x1, s2 += x2, s3 += x3;
             }
-            for (; k < b; k += 32) {
+            for (; k < b; k += TPG) {
                 double x;
                 int c;
                 nz_load<PACKED>(gm, cell, rval, k, c, x);
                 s += beta ? __ddiv_rn(x, __ldg(beta + c)) : x;
             }
             s = (s + s1) + (s2 + s3);
-            mean = __ddiv_rn(bn_warp_sum(s), n); // :1316-1318
+            mean = __ddiv_rn(bn_group_sum<TPG>(s, scratch), n); // :1316-1318
             if (lane == 0 && MU) MU[g] = mean;
             if (mode == 1) continue;
         }
         double ss = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
         int64_t k = a + lane;
-        for (; k + 96 < b; k += 128) {
+        for (; k + 3 * TPG < b; k += 4 * TPG) {
             double x0, x1, x2, x3;
             int c0, c1, c2, c3;
             nz_load<PACKED>(gm, cell, rval, k, c0, x0);
-            nz_load<PACKED>(gm, cell, rval, k + 32, c1, x1);
-            nz_load<PACKED>(gm, cell, rval, k + 64, c2, x2);
-            nz_load<PACKED>(gm, cell, rval, k + 96, c3, x3);
+            nz_load<PACKED>(gm, cell, rval, k + TPG, c1, x1);
+            nz_load<PACKED>(gm, cell, rval, k + 2 * TPG, c2, x2);
+            nz_load<PACKED>(gm, cell, rval, k + 3 * TPG, c3, x3);
             if (beta) {
                 const double b0 = __ldg(beta + c0), b1 = __ldg(beta + c1), b2 = __ldg(beta + c2), b3 = __ldg(beta + c3);
                 x0 = __ddiv_rn(x0, b0), x1 = __ddiv_rn(x1, b1), x2 = __ddiv_rn(x2, b2), x3 = __ddiv_rn(x3, b3);
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
             ss = __dadd_rn(ss, __dmul_rn(d0, d0)), ss1 = __dadd_rn(ss1, __dmul_rn(d1, d1));
             ss2 = __dadd_rn(ss2, __dmul_rn(d2, d2)), ss3 = __dadd_rn(ss3, __dmul_rn(d3, d3));
         }
-        for (; k < b; k += 32) {
+        for (; k < b; k += TPG) {
             double x;
             int c;
             nz_load<PACKED>(gm, cell, rval, k, c, x);
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(256) k_row_moments(int mode, int64_t G, int64_
             const double d = __dsub_rn(v, mean);
             ss = __dadd_rn(ss, __dmul_rn(d, d)); // :1331
         }
-        ss = bn_warp_sum((ss + ss1) + (ss2 + ss3));
+        ss = bn_group_sum<TPG>((ss + ss1) + (ss2 + ss3), scratch);
         if (lane == 0) {
             const double nz = (double)(b - a);
             double var = __dadd_rn(ss, __dmul_rn(__dsub_rn(n, nz), __dmul_rn(mean, mean))); // :1338
@@ -249,10 +253,18 @@ static int launch_row_moments(bn_ctx *ctx, bn_mat *m, int mode, const double *be
 {
     BN_TRY(bn_mat_ensure_csr(ctx, m));
     const int blocks = (int)std::min<int64_t>((m->G + 7) / 8, 148 * 16);
-    if (m->is_count)
-        BN_LAUNCH(ctx, k_row_moments<true>, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->gm, m->cell, m->rval, beta, means_in, MU, SIZE, V);
-    else
-        BN_LAUNCH(ctx, k_row_moments<false>, blocks, 256, 0, mode, m->G, m->C, m->rowptr, m->gm, m->cell, m->rval, beta, means_in, MU, SIZE, V);
+    const int64_t split = 16384; // stored entries from which a gene gets a CTA
+    const bool any_long = m->nnz >= split; // no gene can reach the split otherwise
+    const int blocks_cta = (int)std::min<int64_t>(m->G, 148 * 8);
+#define RM_ARGS mode, split, m->G, m->C, m->rowptr, m->gm, m->cell, m->rval, beta, means_in, MU, SIZE, V
+    if (m->is_count) {
+        if (any_long) BN_LAUNCH(ctx, (k_row_moments<true, 256>), blocks_cta, 256, 0, RM_ARGS);
+        BN_LAUNCH(ctx, (k_row_moments<true, 32>), blocks, 256, 0, RM_ARGS);
+    } else {
+        if (any_long) BN_LAUNCH(ctx, (k_row_moments<false, 256>), blocks_cta, 256, 0, RM_ARGS);
+        BN_LAUNCH(ctx, (k_row_moments<false, 32>), blocks, 256, 0, RM_ARGS);
+    }
+#undef RM_ARGS
     return BN_OK;
 }
 
