@@ -69,6 +69,26 @@ def _vec(a, n=None, name="vector"):
     return a
 
 
+class RMatrix(np.ndarray):
+    """An R matrix with dimnames: a Fortran-ordered float64 array whose columns can also be taken by name
+    (`BB_prior[:, 0]` and `BB_prior["BB_SIZE"]`), e.g. cbind(BB_SIZE, MME_MU) of R/PRIOR_FUNCTIONS.R:298."""
+
+    def __new__(cls, columns, colnames, rownames=None):
+        obj = np.asfortranarray(np.column_stack([np.asarray(c, dtype=_F64) for c in columns])).view(cls)
+        obj.colnames = list(colnames)
+        obj.rownames = None if rownames is None else list(rownames)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.colnames = getattr(obj, "colnames", None)
+        self.rownames = getattr(obj, "rownames", None)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return np.asarray(self)[:, self.colnames.index(key)]
+        return np.asarray(self).__getitem__(key)
+
+
 # --------------------------------------------------------------------------------------
 # context / matrix handles
 # --------------------------------------------------------------------------------------
@@ -520,7 +540,7 @@ class DeviceGroup:
         self.check(self.lib.bn_group_prior(self.h, gm.h, _ptr(b), 1 if BB_SIZE else 0, C.byref(o), C.byref(po)))
         out = {"MME_prior": {"MME_MU": MU, "MME_SIZE": SIZE}, "BETA_vec": b}
         if BB_SIZE:
-            out["BB_prior"] = {"BB_SIZE": BB, "MME_MU": MU}
+            out["BB_prior"] = RMatrix([BB, MU], ["BB_SIZE", "MME_MU"])
             out["MME_SIZE_adjust"] = ADJ
         out["_info"] = {"conv": conv, "nfeval": nfe, "size_lower": po.size_lower, "size_upper": po.size_upper,
                         "coef": tuple(po.coef), "seconds": tuple(po.seconds)}
@@ -629,7 +649,7 @@ def Prior_fun(Data, BETA_vec, parallel=True, NCores=5, FIX_MU=True, GR=False, BB
         ADJ = AdjustSIZE_fun(np.ascontiguousarray(par[:, 0]), MU, SIZE, ctx=ctx)
         if verbose:
             print("Prior estimation has completed!")
-        out = {"MME_prior": base["MME_prior"], "BB_prior": {"size": par[:, 0], "mu": par[:, 1]}, "MME_SIZE_adjust": ADJ,
+        out = {"MME_prior": base["MME_prior"], "BB_prior": RMatrix([par[:, 0], par[:, 1]], ["size", "mu"], M.rownames), "MME_SIZE_adjust": ADJ,
                "BETA_vec": base["BETA_vec"]}
         if return_info:
             out["_info"] = dict(base["_info"], conv=conv, nfeval=nfe, mu_lower=float(rng[0]), mu_upper=float(rng[1]))
@@ -648,7 +668,7 @@ def Prior_fun(Data, BETA_vec, parallel=True, NCores=5, FIX_MU=True, GR=False, BB
     beta_host = b.cpu().numpy() if _is_torch(b) else b
     out = {"MME_prior": {"MME_MU": MU, "MME_SIZE": SIZE}, "BETA_vec": beta_host}
     if BB_SIZE:
-        out["BB_prior"] = {"BB_SIZE": BB, "MME_MU": MU}
+        out["BB_prior"] = RMatrix([BB, MU], ["BB_SIZE", "MME_MU"], M.rownames)   # cbind(BB_SIZE, MME_MU), :298
         out["MME_SIZE_adjust"] = ADJ
         out = {"MME_prior": out["MME_prior"], "BB_prior": out["BB_prior"], "MME_SIZE_adjust": ADJ,
                "BETA_vec": beta_host}

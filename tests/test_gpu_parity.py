@@ -498,7 +498,9 @@ def test_prior_fun_end_to_end(bn, ctx, oracle, small, fixture_data, which):
     assert rel_err(P["MME_prior"]["MME_SIZE"], Po["MME_prior"]["MME_SIZE"]).max() < 1e-6
     assert (rel_err(P["BB_prior"]["BB_SIZE"], Po["BB_prior"]["BB_SIZE"]) <= 1e-6).mean() >= 0.9
     assert rel_err(P["MME_SIZE_adjust"], Po["MME_SIZE_adjust"]).max() < 1e-6
-    assert P["BB_prior"]["MME_MU"] is P["MME_prior"]["MME_MU"]
+    # BB_prior is the reference's G x 2 matrix cbind(BB_SIZE, MME_MU) (R/PRIOR_FUNCTIONS.R:298): columns by position and by name
+    assert P["BB_prior"].shape == (P["MME_prior"]["MME_MU"].shape[0], 2) and P["BB_prior"].colnames == ["BB_SIZE", "MME_MU"]
+    assert np.array_equal(P["BB_prior"]["MME_MU"], P["MME_prior"]["MME_MU"]) and np.array_equal(P["BB_prior"][:, 0], P["BB_prior"]["BB_SIZE"])
     assert P["_info"]["size_upper"] == np.ceil(Po["MME_prior"]["MME_SIZE"].max())
 
 
@@ -1134,7 +1136,7 @@ def test_fit_2d_analytic_gradient_and_prior_fun(bn, ctx, oracle, small):
     X, beta = small["X"][:60, :250], small["beta"][:250]
     P = bn.Prior_fun(X, beta, FIX_MU=False, verbose=False, ctx=ctx, return_info=True)
     Pg = bn.Prior_fun(X, beta, FIX_MU=False, GR=True, verbose=False, ctx=ctx)
-    assert set(P) >= {"MME_prior", "BB_prior", "MME_SIZE_adjust", "BETA_vec"} and set(P["BB_prior"]) == {"size", "mu"}
+    assert set(P) >= {"MME_prior", "BB_prior", "MME_SIZE_adjust", "BETA_vec"} and P["BB_prior"].colnames == ["size", "mu"] and P["BB_prior"].shape[1] == 2
     Po = oracle.Prior_fun(oracle.CSC.from_dense(X), beta, BB_SIZE=False)
     np.testing.assert_allclose(P["MME_prior"]["MME_MU"], Po["MME_prior"]["MME_MU"], rtol=1e-13)
     adj = oracle.AdjustSIZE_fun(P["BB_prior"]["size"], P["MME_prior"]["MME_MU"], P["MME_prior"]["MME_SIZE"])
