@@ -965,7 +965,15 @@ int bn_post_sample_device(bn_ctx *ctx, const bn_mat *m, const double *d_beta, co
     const double rho = (double)m->nnz / ((double)G * (double)m->C);
     const double per_col = (std::max(1.0, rho * (double)G) + (double)nheavy) * (S + 8.0);
     for (int attempt = 0; attempt < 2; attempt++) {
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, (int64_t)(((double)(1 << 30)) / per_col)));
+        int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, (int64_t)(((double)(1 << 30)) / per_col)));
+        // BN_TUNE_SAMPLE_CHUNKS: split the call into at least that many chunks (A/B switch).  Measured on config 5 (calls of 6060
+        // columns): 1 chunk 2748 ms, 2: 2734, 4: 2777, 8: 2823 -- preparing chunk c + 1 next to the main kernel of chunk c buys
+        // nothing once the main kernel fills the SMs; the phase is the sum of its kernels.
+        if (ctx->tune[BN_TUNE_SAMPLE_CHUNKS] > 0) {
+            const int want = ctx->tune[BN_TUNE_SAMPLE_CHUNKS];
+            const int64_t per = ((ncol + want - 1) / want + SM_NCMAX - 1) / SM_NCMAX * SM_NCMAX;
+            chunk = std::min(chunk, std::max<int64_t>(per, SM_NCMAX));
+        }
         // capacity of the gamma-Poisson list (whole blocks of SM_HBLOCK): first attempt 1/8 entry per expected non-zero
         // plus the blocks warps leave partly empty; a chunk that overflows makes the whole call repeat with worst-case lists
         const double per_elem = attempt == 0 ? std::min(1.0, std::max(1.0 / 64, 0.125 * rho)) : 1.0;

@@ -323,8 +323,10 @@ BN_API int bn_debug_dense_table(bn_ctx *ctx, const double *BETA, int64_t C, doub
  *                         at most 20 % non-zeros, first generation otherwise (see bn_debug_last_fit)
  *   BN_TUNE_SAMPLE_NCS    columns walked per CTA by the 3-D sampler
  *   BN_TUNE_SAMPLE_SERIAL 1: the 3-D sampler queues every kernel on the context's stream (no side streams)
- *   BN_TUNE_FIT_SPLIT     version 2 of the fit: genes with at least this many stored entries get a CTA, the others a warp */
-enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_SAMPLE_SERIAL = 3, BN_TUNE_FIT_SPLIT = 4, BN_TUNE_COUNT = 8 };
+ *   BN_TUNE_FIT_SPLIT     version 2 of the fit: genes with at least this many stored entries get a CTA, the others a warp
+ *   BN_TUNE_SAMPLE_CHUNKS the 3-D sampler splits a call into at least this many column chunks (default: by side-buffer size only) */
+enum { BN_TUNE_FIT_VARIANT = 0, BN_TUNE_SAMPLE_NCS = 1, BN_TUNE_POST_NCS = 2, BN_TUNE_SAMPLE_SERIAL = 3, BN_TUNE_FIT_SPLIT = 4, BN_TUNE_SAMPLE_CHUNKS = 5,
+       BN_TUNE_COUNT = 8 };
 BN_API int bn_debug_tune(bn_ctx *ctx, int knob, int value);
 /* One raw Philox4x32-10 block (counter ctr[4], key[2]) -> out[4]; lets tests pin the
  * generator against the published known-answer vectors. */
