@@ -224,16 +224,10 @@ def run_ours(args):
     Gt, C, S, groups = cfg["G"], cfg["C"], cfg["S"], cfg["groups"]
     strong = args.config == 5 and not args.weak          # config 5: ONE matrix, gene blocks of G / N
     if strong:
-        if world > 1:
-            # gene blocks of equal COST, not equal size: the posterior costs ~C per gene, the prior (gene-major build, moments,
-            # fit version 2) ~1.5 per stored entry (measured on config 5: 83 us per gene and 0.093 ns per entry); the entries of a
-            # gene are estimated from the generator's parameters (P(x > 0) at the mean BETA) -- expression is heavy-tailed, so
-            # blocks of equal size differ 2.6x in entries (fit 41 - 109 ms over 8 ranks before this)
-            mu_g, size_g, beta_g = synth_params(Gt, C, cfg["m0"])
-            nnz_g = C * (1.0 - (size_g / (size_g + mu_g * beta_g.mean())) ** size_g)
-            bounds = [int(b) for b in bdist.balanced_gene_blocks(nnz_g, world, n_cells=C, nnz_weight=1.5)]
-        else:
-            bounds = [0, Gt]
+        # equal gene blocks: with the genes in the generator's (random) order their stored entries differ by +-3 % between
+        # blocks of 4125 genes; the fit's imbalance over ranks came from single long genes late in the queue, which the
+        # longest-first gene lists removed.  (dist.balanced_gene_blocks is for real matrices, whose gene order is not random.)
+        bounds = [(Gt * k) // world for k in range(world + 1)]
         g0, G = bounds[rank], bounds[rank + 1] - bounds[rank]
         G_total = Gt
     else:
@@ -452,7 +446,8 @@ def run_e2e(args, bn, ctx, cfg, mu, size, beta_gen, g0, G, world, dev, barrier_s
     if args.no_e2e:
         return None
     C, S, lib = cfg["C"], cfg["S"], ctx.lib
-    per_cell = posterior_elements(G, 1, cfg) * 8
+    # the same cell count on every rank (the BETA all-reduce spans the cells): sized for the largest gene block
+    per_cell = posterior_elements(int(allmax(float(G))), 1, cfg) * 8
     cells = int(min(C, max(64, (args.e2e_out_gb * 2 ** 30) // per_cell)))
     if cfg["groups"] > 1:
         cells = C // cfg["groups"]                     # one condition group: a GG run on its cells
