@@ -64,7 +64,7 @@ __device__ __forceinline__ double post_mode(double x, double size, double mu, do
 // (bn_mat_ensure_blockptr: two coalesced loads per column instead of a binary search), so slice lengths are
 // known and up to PF x 32 non-zeros are prefetched into registers one column ahead; size/mu of the warp's genes
 // stay in registers.  EPL = 4 (64 registers, 4 CTAs per SM) measured best: mode on the 50 % dense config
-// 0.93 -> 0.66 ms against the CTA-synchronous k_posterior above (kept behind BN_POST_V1 for A/B runs).
+// 0.93 -> 0.66 ms against the first, CTA-synchronous kernel (removed).
 // ---------------------------------------------------------------------------------
 #define PW_WARPS 8
 
