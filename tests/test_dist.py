@@ -20,6 +20,10 @@ def test_balanced_gene_blocks():
         assert b[0] == 0 and b[-1] == 5000 and (np.diff(b) > 0).all() and len(b) == world + 1
         cost = np.add.reduceat(1000 + 4.0 * nnz, b[:-1])
         assert cost.max() / cost.mean() < 1.25
+    # the weight of a stored entry against a cell is the caller's (4: first-generation fit, ~1.5: fit version 2 with S = 20 draws)
+    heavy = np.r_[np.full(10, 10000.0), np.zeros(990)]
+    b4, b0 = dist.balanced_gene_blocks(heavy, 2, n_cells=100, nnz_weight=4.0), dist.balanced_gene_blocks(heavy, 2, n_cells=100, nnz_weight=0.0)
+    assert b0[1] == 500 and b4[1] < 20                 # weight 0: equal gene counts; weight 4: the ten heavy genes are half the cost
     b = dist.balanced_gene_blocks(np.zeros(3), 3)
     assert list(b) == [0, 1, 2, 3]
 
