@@ -576,7 +576,7 @@ class GroupMatrix:
 # --------------------------------------------------------------------------------------
 # R-level functions
 # --------------------------------------------------------------------------------------
-TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS, TUNE_SAMPLE_SERIAL = 0, 1, 2, 3
+TUNE_FIT_VARIANT, TUNE_SAMPLE_NCS, TUNE_POST_NCS, TUNE_SAMPLE_SERIAL, TUNE_FIT_SPLIT, TUNE_SAMPLE_CHUNKS = 0, 1, 2, 3, 4, 5
 
 
 def _fit_opts(GR=False, method="spg", maxfeval=500, park_after=0):
